@@ -1,0 +1,191 @@
+/* libsb_cuda — C ABI of the B200-native pattern/ reduce/scan library.
+ *
+ * This header is the lower drop-in boundary.  Every entry point states the
+ * reference interface it replaces as `file:line` inside /root/reference (unisa-hpc/sycl-bench
+ * 2.0.4).  The reference has no library layer: its device code is inline SYCL lambdas inside the
+ * benchmark classes, submitted through `sycl::queue::submit`.  libsb_cuda is what a maintainer
+ * binds behind those `submit` call sites (INTEGRATION.md shows the exact stubs).
+ *
+ * Conventions
+ *  - plain C, `extern "C"`, pointers + sizes only; no C++/torch types.
+ *  - every data pointer of an `sb_<op>_<T>` call is a DEVICE-accessible pointer owned by the
+ *    caller (cudaMalloc, or pinned+mapped host memory); the library never allocates per call.
+ *  - calls are ASYNCHRONOUS on the ctx stream (like `queue.submit`, include/common.h:70-75 waits
+ *    afterwards); results stay in device memory (pattern/reduction.cpp:60,96).
+ *  - return value: 0 = ok; negative = sb_status below; positive = cudaError_t passed through.
+ *    No C++ exception crosses this ABI.
+ *  - a ctx is single-threaded; distinct ctxs are independent.
+ *  - there is NO CPU fallback: without a CUDA device sb_ctx_create fails with SB_ERR_NO_DEVICE.
+ *
+ * Type suffixes follow include/type_traits.h:14-23 of the reference:
+ *    i16 = short ("int16"), i32 = int ("int32"), i64 = long long ("int64"),
+ *    f32 = float ("fp32"),  f64 = double ("fp64").
+ */
+#ifndef SB_CUDA_H
+#define SB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define SB_VERSION 100 /* 0.1.0 */
+
+typedef struct sb_ctx sb_ctx;
+
+enum sb_status {
+  SB_OK = 0,
+  SB_ERR_BAD_ARG = -1,     /* null pointer, n too large, bad enum                              */
+  SB_ERR_MISALIGNED = -2,  /* pointer not aligned to sizeof(T)                                 */
+  SB_ERR_WORKSPACE = -3,   /* internal workspace allocation failed                             */
+  SB_ERR_SEG_LEN = -4,     /* seg_len == 0, or n % seg_len != 0 where the reference asserts it */
+  SB_ERR_NO_DEVICE = -5,   /* no CUDA device / device index out of range                       */
+  SB_ERR_UNSUPPORTED = -6, /* device is not sm_100 (library is built for sm_100a only)         */
+  SB_ERR_TIMER = -7        /* sb_timer_end without sb_timer_begin                              */
+};
+
+enum sb_dtype { SB_I16 = 0, SB_I32 = 1, SB_I64 = 2, SB_F32 = 3, SB_F64 = 4 };
+enum sb_op { SB_OP_REDUCE = 0, SB_OP_SCAN = 1, SB_OP_SEGREDUCE = 2, SB_OP_SEGSCAN = 3 };
+
+/* ---- library / context ---------------------------------------------------------------------- */
+
+int sb_version(void);
+const char* sb_strerror(int status);
+
+/* Number of CUDA devices (replaces the device selectors of include/command_line.h:182-202). */
+int sb_device_count(int* count);
+
+/* One ctx per (device, stream): the counterpart of `BenchmarkArgs::device_queue`
+ * (include/command_line.h:133,152-154).  `stream` is a cudaStream_t (NULL = a new non-blocking
+ * stream owned by the ctx).  The ctx owns the scratch the kernels need (block partials, tile
+ * descriptors, tickets), sized once for the device, so that op calls never allocate. */
+int sb_ctx_create(int device, void* stream, sb_ctx** out);
+int sb_ctx_destroy(sb_ctx* ctx);
+int sb_ctx_set_stream(sb_ctx* ctx, void* stream);
+void* sb_ctx_stream(sb_ctx* ctx);
+/* queue.wait_and_throw(): include/common.h:61,75. */
+int sb_ctx_sync(sb_ctx* ctx);
+/* device-name CSV column: include/common.h:42-43. */
+int sb_ctx_device_name(sb_ctx* ctx, char* buf, size_t buflen);
+int sb_ctx_sm_count(sb_ctx* ctx);
+/* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+uint64_t sb_ctx_launch_count(sb_ctx* ctx);
+/* Bytes of device scratch the ctx holds / that an op on n elements touches. */
+size_t sb_workspace_bytes(int op, int dtype, size_t n);
+
+/* CUDA-event timing on the ctx stream; replaces the SYCL event profiling of
+ * include/common.h:83-101 (kernel-time).  begin/end may bracket any number of sb_* calls. */
+int sb_timer_begin(sb_ctx* ctx);
+int sb_timer_end(sb_ctx* ctx, float* elapsed_ms); /* synchronises on the end event */
+
+/* ---- memory helpers (PrefetchedBuffer, include/memory_wrappers.h:39-92) --------------------- */
+
+int sb_malloc(sb_ctx* ctx, void** dptr, size_t bytes);       /* initialize(q, range)  :42-45 */
+int sb_free(sb_ctx* ctx, void* dptr);
+int sb_host_alloc(sb_ctx* ctx, void** hptr, size_t bytes);   /* pinned + mapped host memory   */
+int sb_host_free(sb_ctx* ctx, void* hptr);
+int sb_memcpy_h2d(sb_ctx* ctx, void* dst, const void* src, size_t bytes); /* :47-57, async */
+int sb_memcpy_d2h(sb_ctx* ctx, void* dst, const void* src, size_t bytes); /* get_host_access :81 */
+int sb_memset(sb_ctx* ctx, void* dst, int byte, size_t bytes);
+
+/* ---- generate_input on the device ----------------------------------------------------------- */
+/* out[i] = static_cast<T>(offset + i)   (pattern/reduction.cpp:31-34,
+ * pattern/segmentedreduction.cpp:25-28).  `offset` is the global index of the shard's first
+ * element (multi-GPU).  Integer types wrap, fp32/fp64 round to nearest even like x86 cvtsi2ss. */
+int sb_iota_i16(sb_ctx*, int16_t* out, size_t n, uint64_t offset);
+int sb_iota_i32(sb_ctx*, int32_t* out, size_t n, uint64_t offset);
+int sb_iota_i64(sb_ctx*, int64_t* out, size_t n, uint64_t offset);
+int sb_iota_f32(sb_ctx*, float* out, size_t n, uint64_t offset);
+int sb_iota_f64(sb_ctx*, double* out, size_t n, uint64_t offset);
+
+/* ---- reduction ------------------------------------------------------------------------------ */
+/* out[0] = sum(in[0..n)), one launch.  Replaces the whole multi-pass driver
+ * Reduction<T>::submit (pattern/reduction.cpp:71-97) and both kernels
+ * local_reduce_ndrange (:99-126) / local_reduce_hierarchical (:128-167).
+ * Integers wrap mod 2^w (bit-exact with the reference for any order).  Floating point uses a
+ * fixed (deterministic) order that differs from the reference's tree; see DESIGN.md tolerance.
+ * n == 0 writes 0.  `out` must not alias `in`. */
+int sb_reduce_i32(sb_ctx*, const int32_t* in, size_t n, int32_t* out);
+int sb_reduce_i64(sb_ctx*, const int64_t* in, size_t n, int64_t* out);
+int sb_reduce_f32(sb_ctx*, const float* in, size_t n, float* out);
+int sb_reduce_f64(sb_ctx*, const double* in, size_t n, double* out);
+
+/* ---- segmented reduction -------------------------------------------------------------------- */
+/* In place, reference layout (pattern/segmentedreduction.cpp:35-61,63-96; contract :112-119):
+ *   inout[g*seg_len] = tree_sum(inout[g*seg_len .. g*seg_len+seg_len-1]),   other elements untouched.
+ * n % seg_len must be 0 (the reference asserts it, :23).  For a seg_len that is not a power of
+ * two the reference's halving tree silently skips elements; the same subset is summed here
+ * (oracle/sb_oracle.c: ref_tree_member).  */
+int sb_segreduce_i16(sb_ctx*, int16_t* inout, size_t n, size_t seg_len);
+int sb_segreduce_i32(sb_ctx*, int32_t* inout, size_t n, size_t seg_len);
+int sb_segreduce_i64(sb_ctx*, int64_t* inout, size_t n, size_t seg_len);
+int sb_segreduce_f32(sb_ctx*, float* inout, size_t n, size_t seg_len);
+int sb_segreduce_f64(sb_ctx*, double* inout, size_t n, size_t seg_len);
+
+/* ---- scan / prefix sum ---------------------------------------------------------------------- */
+/* pattern/prefixsum.cpp:1 and pattern/scan.cpp:1 are TODO stubs upstream; semantics are the ones
+ * written down in DESIGN.md §Scan semantics (parity unpinned upstream).
+ *   group_len == 0 : global scan, single pass, decoupled look-back.
+ *   group_len  > 0 : the scan restarts every group_len elements ("per-work-group granularity").
+ *   exclusive != 0 : out[i] = sum of the elements strictly before i (0 at a restart).
+ * `seed` (device pointer, may be NULL) is added to every output of a global scan: the carry-in of
+ * a shard in the multi-GPU path.  in == out (in place) is allowed. */
+int sb_scan_i32(sb_ctx*, const int32_t* in, int32_t* out, size_t n, int exclusive, size_t group_len, const int32_t* seed);
+int sb_scan_i64(sb_ctx*, const int64_t* in, int64_t* out, size_t n, int exclusive, size_t group_len, const int64_t* seed);
+int sb_scan_f32(sb_ctx*, const float* in, float* out, size_t n, int exclusive, size_t group_len, const float* seed);
+int sb_scan_f64(sb_ctx*, const double* in, double* out, size_t n, int exclusive, size_t group_len, const double* seed);
+
+/* ---- segmented scan ------------------------------------------------------------------------- */
+/* pattern/segmentedscan.cpp:1 is a TODO stub upstream (DESIGN.md §Scan semantics).
+ * Sum-scan that restarts at segment heads.  head_flags == NULL: heads are implicit at
+ * i % seg_len == 0.  head_flags != NULL: one uint8 per element, non-zero marks a head
+ * (seg_len is ignored; element 0 is always a head).  Operator on (value, flag) pairs:
+ * (v1,f1) (+) (v2,f2) = (f2 ? v2 : v1+v2, f1|f2). */
+int sb_segscan_i32(sb_ctx*, const int32_t* in, int32_t* out, size_t n, size_t seg_len, const uint8_t* head_flags, int exclusive);
+int sb_segscan_i64(sb_ctx*, const int64_t* in, int64_t* out, size_t n, size_t seg_len, const uint8_t* head_flags, int exclusive);
+int sb_segscan_f32(sb_ctx*, const float* in, float* out, size_t n, size_t seg_len, const uint8_t* head_flags, int exclusive);
+int sb_segscan_f64(sb_ctx*, const double* in, double* out, size_t n, size_t seg_len, const uint8_t* head_flags, int exclusive);
+
+/* ---- multi-GPU carry ------------------------------------------------------------------------ */
+/* inout[i] += carry[0]  (the "fused carry-add pass" of BASELINE.json north_star). */
+int sb_carry_add_i32(sb_ctx*, int32_t* inout, size_t n, const int32_t* carry);
+int sb_carry_add_i64(sb_ctx*, int64_t* inout, size_t n, const int64_t* carry);
+int sb_carry_add_f32(sb_ctx*, float* inout, size_t n, const float* carry);
+int sb_carry_add_f64(sb_ctx*, double* inout, size_t n, const double* carry);
+/* carry_out[0] = sum(totals[0..rank))  — turns the all-gathered shard totals into this rank's
+ * exclusive carry on the device (no host round trip). */
+int sb_exclusive_carry_i32(sb_ctx*, const int32_t* totals, int rank, int32_t* carry_out);
+int sb_exclusive_carry_i64(sb_ctx*, const int64_t* totals, int rank, int64_t* carry_out);
+int sb_exclusive_carry_f32(sb_ctx*, const float* totals, int rank, float* carry_out);
+int sb_exclusive_carry_f64(sb_ctx*, const double* totals, int rank, double* carry_out);
+
+/* ---- on-device verification against the closed forms of the iota input ------ */
+/* Counts elements of `data` (a result computed from in[i] = (T)(offset+i)) that differ from the
+ * closed form; integer types only (mod 2^w).  mismatches is a DEVICE pointer to one uint64.
+ *   kind 0: inclusive scan   kind 1: exclusive scan   (seg_len == 0: global; else restart every seg_len)
+ *   kind 2: segmented-reduction layout (head = segment sum, others = input). */
+int sb_check_iota_i32(sb_ctx*, const int32_t* data, size_t n, uint64_t offset, int kind, size_t seg_len, uint64_t* mismatches);
+int sb_check_iota_i64(sb_ctx*, const int64_t* data, size_t n, uint64_t offset, int kind, size_t seg_len, uint64_t* mismatches);
+
+/* ---- host-buffer (end-to-end) entry points -------------------------------------------------- */
+/* Same operations on HOST buffers: H2D of the input, the kernel, D2H of the result, all on the ctx
+ * stream, synchronous on return.  This is the call shape of the reference plugin where setup()
+ * uploads a host std::vector (pattern/reduction.cpp:36-42) and verify() reads the result back
+ * (:60).  Device staging buffers are cached in the ctx and grow on demand. */
+int sb_host_reduce(sb_ctx*, int dtype, const void* h_in, size_t n, void* h_out);
+int sb_host_scan(sb_ctx*, int dtype, const void* h_in, void* h_out, size_t n, int exclusive, size_t group_len);
+int sb_host_segreduce(sb_ctx*, int dtype, void* h_inout, size_t n, size_t seg_len);
+int sb_host_segscan(sb_ctx*, int dtype, const void* h_in, void* h_out, size_t n, size_t seg_len, const uint8_t* h_head_flags, int exclusive);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* SB_CUDA_H */

@@ -1,0 +1,139 @@
+// libsb_cuda internals shared by all translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/sb_cuda.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libsb_cuda is written for sm_100a (B200) only"
+#endif
+
+#define SB_FULL_MASK 0xffffffffu
+
+struct sb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 0;
+  uint64_t launches = 0;
+
+  // reduce: per-block partials (8 B each) + completion ticket
+  void* partials = nullptr;
+  size_t partials_slots = 0;
+  unsigned int* reduce_ticket = nullptr;
+
+  // scan: tile descriptors (separate arrays for 64-bit and 128-bit descriptors), dynamic tile ticket
+  void* desc64 = nullptr;
+  size_t desc64_count = 0;
+  void* desc128 = nullptr;
+  size_t desc128_count = 0;
+  unsigned long long* scan_ticket = nullptr;  // monotonically increasing, never reset
+  unsigned long long scan_ticket_base = 0;    // host mirror of the value the next launch starts at
+  uint32_t scan_epoch = 0;                    // descriptor generation, bumped per launch
+
+  // timing
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  bool timing = false;
+
+  // host-buffer entry points: cached device staging
+  void* stage[2] = {nullptr, nullptr};
+  size_t stage_bytes[2] = {0, 0};
+  void* stage_small = nullptr;  // 64 B result slot
+};
+
+#define SB_CUDA_TRY(expr)                      \
+  do {                                         \
+    cudaError_t _e = (expr);                   \
+    if(_e != cudaSuccess) return (int)_e;      \
+  } while(0)
+
+#define SB_CHECK_LAUNCH(ctx)                   \
+  do {                                         \
+    (ctx)->launches++;                         \
+    cudaError_t _e = cudaGetLastError();       \
+    if(_e != cudaSuccess) return (int)_e;      \
+  } while(0)
+
+struct sb_device_guard {
+  int prev = -1;
+  explicit sb_device_guard(int dev) {
+    cudaGetDevice(&prev);
+    if(prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~sb_device_guard() {
+    if(prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---- arithmetic type mapping: integers are summed as unsigned (wrap mod 2^w, no UB) -------------
+template <typename T> struct sb_arith { using type = T; };
+template <> struct sb_arith<int16_t> { using type = uint16_t; };
+template <> struct sb_arith<int32_t> { using type = uint32_t; };
+template <> struct sb_arith<int64_t> { using type = unsigned long long; };
+template <> struct sb_arith<long long> { using type = unsigned long long; };
+
+namespace sb {
+
+template <typename T> struct vec_of { static constexpr int N = 16 / sizeof(T); };
+
+// 16-byte register tile of a thread
+template <typename T>
+struct alignas(16) Vec {
+  static constexpr int N = 16 / sizeof(T);
+  T v[N];
+};
+
+// streaming 128-bit load, read-only path (input is never written by the kernel)
+template <typename T>
+__device__ __forceinline__ Vec<T> ldg_nc(const T* p) {
+  uint4 r;
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return *reinterpret_cast<Vec<T>*>(&r);
+}
+// streaming 128-bit load through the coherent path (buffer may be written by this kernel)
+template <typename T>
+__device__ __forceinline__ Vec<T> ldg_stream(const T* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return *reinterpret_cast<Vec<T>*>(&r);
+}
+template <typename T>
+__device__ __forceinline__ void stg_vec(T* p, const Vec<T>& v) {
+  const uint4& r = *reinterpret_cast<const uint4*>(&v);
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// warp sum: redux.sync for 32-bit integers, xor-shuffle tree otherwise
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for(int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(SB_FULL_MASK, v, d);
+  return v;
+}
+template <>
+__device__ __forceinline__ uint32_t warp_sum<uint32_t>(uint32_t v) {
+  return __reduce_add_sync(SB_FULL_MASK, v);
+}
+template <>
+__device__ __forceinline__ uint16_t warp_sum<uint16_t>(uint16_t v) {
+  return (uint16_t)__reduce_add_sync(SB_FULL_MASK, (uint32_t)v);
+}
+
+template <typename T>
+__device__ __forceinline__ T shfl_up(T v, int d) { return __shfl_up_sync(SB_FULL_MASK, v, d); }
+template <typename T>
+__device__ __forceinline__ T shfl_idx(T v, int l) { return __shfl_sync(SB_FULL_MASK, v, l); }
+
+inline bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
+inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace sb
+
+// workspace growth helpers (sb_ctx.cu)
+int sb_ctx_reserve_desc(sb_ctx* ctx, size_t count64, size_t count128);
+int sb_ctx_reserve_stage(sb_ctx* ctx, int which, size_t bytes);

@@ -1,0 +1,176 @@
+// Device-side input generation, multi-GPU carry helpers and closed-form verification.
+//  - sb_iota_<T>      : generate_input on the device (/root/reference/pattern/reduction.cpp:31-34,
+//                       pattern/segmentedreduction.cpp:25-28), needed because 2^33 elements
+//                       (32 GiB) cannot be staged through the host.
+//  - sb_carry_add_<T> : the "fused carry-add pass" of the multi-GPU prefix sum (BASELINE.json).
+//  - sb_check_iota_<T>: verify() against the closed forms of SURVEY.md A.4, on the device.
+#include "sb_common.cuh"
+
+namespace {
+
+constexpr int UT_NT = 256;
+
+template <typename A> __device__ __forceinline__ A cast_index(unsigned long long g) { return (A)g; }
+
+template <typename A>
+__global__ void __launch_bounds__(UT_NT) iota_kernel(A* __restrict__ out, size_t n, unsigned long long offset, int aligned) {
+  constexpr int VEC = 16 / sizeof(A);
+  const size_t stride = (size_t)gridDim.x * UT_NT * VEC;
+  for(size_t i = ((size_t)blockIdx.x * UT_NT + threadIdx.x) * VEC; i < n; i += stride) {
+    if(aligned && i + VEC <= n) {
+      sb::Vec<A> v;
+#pragma unroll
+      for(int c = 0; c < VEC; ++c) v.v[c] = cast_index<A>(offset + i + c);
+      sb::stg_vec<A>(out + i, v);
+    } else {
+#pragma unroll
+      for(int c = 0; c < VEC; ++c)
+        if(i + c < n) out[i + c] = cast_index<A>(offset + i + c);
+    }
+  }
+}
+
+template <typename A>
+__global__ void __launch_bounds__(UT_NT) carry_add_kernel(A* __restrict__ buf, size_t n, const A* __restrict__ carry, int aligned) {
+  constexpr int VEC = 16 / sizeof(A);
+  constexpr int U = 4;
+  const A c0 = *carry;
+  const size_t nvec = aligned ? n / VEC : 0;
+  const size_t stride = (size_t)gridDim.x * UT_NT * U;
+  for(size_t b = (size_t)blockIdx.x * UT_NT * U + threadIdx.x; b < nvec; b += stride) {
+    sb::Vec<A> t[U];
+#pragma unroll
+    for(int u = 0; u < U; ++u)
+      if(b + (size_t)u * UT_NT < nvec) t[u] = sb::ldg_stream<A>(buf + (b + (size_t)u * UT_NT) * VEC);
+#pragma unroll
+    for(int u = 0; u < U; ++u)
+      if(b + (size_t)u * UT_NT < nvec) {
+#pragma unroll
+        for(int c = 0; c < VEC; ++c) t[u].v[c] += c0;
+        sb::stg_vec<A>(buf + (b + (size_t)u * UT_NT) * VEC, t[u]);
+      }
+  }
+  // scalar remainder
+  const size_t rem_begin = nvec * VEC;
+  for(size_t i = rem_begin + (size_t)blockIdx.x * UT_NT + threadIdx.x; i < n; i += (size_t)gridDim.x * UT_NT) buf[i] += c0;
+}
+
+template <typename A>
+__global__ void exclusive_carry_kernel(const A* __restrict__ totals, int rank, A* __restrict__ carry_out) {
+  if(threadIdx.x == 0 && blockIdx.x == 0) {
+    A c = A(0);
+    for(int r = 0; r < rank; ++r) c += totals[r];
+    *carry_out = c;
+  }
+}
+
+// g*(g+1)/2 mod 2^64 without overflowing the intermediate product
+__device__ __forceinline__ unsigned long long tri(unsigned long long g) {
+  return (g & 1ull) ? g * ((g + 1ull) >> 1) : (g >> 1) * (g + 1ull);
+}
+
+template <typename A>
+__global__ void __launch_bounds__(UT_NT) check_iota_kernel(const A* __restrict__ data, size_t n, unsigned long long offset, int kind,
+    unsigned long long seg_len, unsigned long long* __restrict__ mismatches) {
+  unsigned int bad = 0;
+  const size_t stride = (size_t)gridDim.x * UT_NT;
+  for(size_t i = (size_t)blockIdx.x * UT_NT + threadIdx.x; i < n; i += stride) {
+    const unsigned long long g = offset + i;
+    unsigned long long expect;
+    if(seg_len == 0) {
+      expect = (kind == 0) ? tri(g) : (g == 0 ? 0ull : tri(g - 1ull));
+    } else {
+      const unsigned long long q = g / seg_len, j = g - q * seg_len;
+      if(kind == 0) expect = q * seg_len * (j + 1ull) + tri(j);
+      else if(kind == 1) expect = q * seg_len * j + (j == 0 ? 0ull : tri(j - 1ull));
+      else expect = (j == 0) ? q * seg_len * seg_len + tri(seg_len - 1ull) : g;
+    }
+    if(data[i] != (A)expect) ++bad;
+  }
+  bad = __reduce_add_sync(SB_FULL_MASK, bad);
+  if((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+size_t grid_for(sb_ctx* ctx, size_t work_items, size_t per_block) {
+  size_t blocks = (work_items + per_block - 1) / per_block;
+  const size_t cap = (size_t)ctx->sm_count * 8;
+  if(blocks > cap) blocks = cap;
+  return blocks ? blocks : 1;
+}
+
+template <typename T>
+int iota_impl(sb_ctx* ctx, T* out, size_t n, uint64_t offset) {
+  using A = typename sb_arith<T>::type;
+  if(!ctx || (n && !out)) return SB_ERR_BAD_ARG;
+  if(!sb::aligned_to(out, sizeof(T))) return SB_ERR_MISALIGNED;
+  if(n == 0) return SB_OK;
+  sb_device_guard guard(ctx->device);
+  constexpr int VEC = 16 / sizeof(T);
+  const size_t blocks = grid_for(ctx, n, (size_t)UT_NT * VEC);
+  iota_kernel<A><<<(unsigned)blocks, UT_NT, 0, ctx->stream>>>(reinterpret_cast<A*>(out), n, offset, sb::aligned_to(out, 16) ? 1 : 0);
+  SB_CHECK_LAUNCH(ctx);
+  return SB_OK;
+}
+
+template <typename T>
+int carry_add_impl(sb_ctx* ctx, T* inout, size_t n, const T* carry) {
+  using A = typename sb_arith<T>::type;
+  if(!ctx || !carry || (n && !inout)) return SB_ERR_BAD_ARG;
+  if(!sb::aligned_to(inout, sizeof(T)) || !sb::aligned_to(carry, sizeof(T))) return SB_ERR_MISALIGNED;
+  if(n == 0) return SB_OK;
+  sb_device_guard guard(ctx->device);
+  constexpr int VEC = 16 / sizeof(T);
+  const size_t blocks = grid_for(ctx, n, (size_t)UT_NT * VEC * 4);
+  carry_add_kernel<A><<<(unsigned)blocks, UT_NT, 0, ctx->stream>>>(
+      reinterpret_cast<A*>(inout), n, reinterpret_cast<const A*>(carry), sb::aligned_to(inout, 16) ? 1 : 0);
+  SB_CHECK_LAUNCH(ctx);
+  return SB_OK;
+}
+
+template <typename T>
+int exclusive_carry_impl(sb_ctx* ctx, const T* totals, int rank, T* carry_out) {
+  using A = typename sb_arith<T>::type;
+  if(!ctx || !totals || !carry_out || rank < 0) return SB_ERR_BAD_ARG;
+  sb_device_guard guard(ctx->device);
+  exclusive_carry_kernel<A><<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const A*>(totals), rank, reinterpret_cast<A*>(carry_out));
+  SB_CHECK_LAUNCH(ctx);
+  return SB_OK;
+}
+
+template <typename T>
+int check_impl(sb_ctx* ctx, const T* data, size_t n, uint64_t offset, int kind, size_t seg_len, uint64_t* mismatches) {
+  using A = typename sb_arith<T>::type;
+  if(!ctx || !mismatches || (n && !data) || kind < 0 || kind > 2) return SB_ERR_BAD_ARG;
+  if(kind == 2 && (seg_len == 0 || !sb::is_pow2(seg_len))) return SB_ERR_SEG_LEN;
+  sb_device_guard guard(ctx->device);
+  SB_CUDA_TRY(cudaMemsetAsync(mismatches, 0, sizeof(uint64_t), ctx->stream));
+  if(n == 0) return SB_OK;
+  const size_t blocks = grid_for(ctx, n, (size_t)UT_NT * 8);
+  check_iota_kernel<A><<<(unsigned)blocks, UT_NT, 0, ctx->stream>>>(
+      reinterpret_cast<const A*>(data), n, offset, kind, seg_len, reinterpret_cast<unsigned long long*>(mismatches));
+  SB_CHECK_LAUNCH(ctx);
+  return SB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+int sb_iota_i16(sb_ctx* c, int16_t* o, size_t n, uint64_t off) { return iota_impl<int16_t>(c, o, n, off); }
+int sb_iota_i32(sb_ctx* c, int32_t* o, size_t n, uint64_t off) { return iota_impl<int32_t>(c, o, n, off); }
+int sb_iota_i64(sb_ctx* c, int64_t* o, size_t n, uint64_t off) { return iota_impl<int64_t>(c, o, n, off); }
+int sb_iota_f32(sb_ctx* c, float* o, size_t n, uint64_t off) { return iota_impl<float>(c, o, n, off); }
+int sb_iota_f64(sb_ctx* c, double* o, size_t n, uint64_t off) { return iota_impl<double>(c, o, n, off); }
+
+int sb_carry_add_i32(sb_ctx* c, int32_t* p, size_t n, const int32_t* k) { return carry_add_impl<int32_t>(c, p, n, k); }
+int sb_carry_add_i64(sb_ctx* c, int64_t* p, size_t n, const int64_t* k) { return carry_add_impl<int64_t>(c, p, n, k); }
+int sb_carry_add_f32(sb_ctx* c, float* p, size_t n, const float* k) { return carry_add_impl<float>(c, p, n, k); }
+int sb_carry_add_f64(sb_ctx* c, double* p, size_t n, const double* k) { return carry_add_impl<double>(c, p, n, k); }
+
+int sb_exclusive_carry_i32(sb_ctx* c, const int32_t* t, int r, int32_t* o) { return exclusive_carry_impl<int32_t>(c, t, r, o); }
+int sb_exclusive_carry_i64(sb_ctx* c, const int64_t* t, int r, int64_t* o) { return exclusive_carry_impl<int64_t>(c, t, r, o); }
+int sb_exclusive_carry_f32(sb_ctx* c, const float* t, int r, float* o) { return exclusive_carry_impl<float>(c, t, r, o); }
+int sb_exclusive_carry_f64(sb_ctx* c, const double* t, int r, double* o) { return exclusive_carry_impl<double>(c, t, r, o); }
+
+int sb_check_iota_i32(sb_ctx* c, const int32_t* d, size_t n, uint64_t off, int kind, size_t L, uint64_t* m) { return check_impl<int32_t>(c, d, n, off, kind, L, m); }
+int sb_check_iota_i64(sb_ctx* c, const int64_t* d, size_t n, uint64_t off, int kind, size_t L, uint64_t* m) { return check_impl<int64_t>(c, d, n, off, kind, L, m); }
+}

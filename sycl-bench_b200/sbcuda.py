@@ -1,0 +1,252 @@
+"""ctypes view of libsb_cuda (include/sb_cuda.h).  Plumbing only — no compute, no fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+
+DTYPES = ("i16", "i32", "i64", "f32", "f64")
+_DTYPE_ENUM = {"i16": 0, "i32": 1, "i64": 2, "f32": 3, "f64": 4}
+_DTYPE_SIZE = {"i16": 2, "i32": 4, "i64": 8, "f32": 4, "f64": 8}
+
+
+class SbError(RuntimeError):
+    def __init__(self, status: int, what: str):
+        super().__init__(f"libsb_cuda error {status}: {what}")
+        self.status = status
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "lib", "libsb_cuda.so")
+
+
+def header_path() -> str:
+    return os.path.join(_ROOT, "include", "sb_cuda.h")
+
+
+def declared_symbols() -> list[str]:
+    """Every function include/sb_cuda.h declares."""
+    text = open(header_path()).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libsb_cuda.so from the tree.  Raises loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is missing: build it with `make -C sycl-bench_b200` or __graft_entry__.build(). "
+            "There is no CPU or PyTorch fallback."
+        )
+    L = C.CDLL(path)
+    vp, sz, i, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+    L.sb_version.restype = i
+    L.sb_strerror.restype = C.c_char_p
+    L.sb_strerror.argtypes = [i]
+    L.sb_device_count.argtypes = [C.POINTER(i)]
+    L.sb_ctx_create.argtypes = [i, vp, C.POINTER(vp)]
+    L.sb_ctx_destroy.argtypes = [vp]
+    L.sb_ctx_set_stream.argtypes = [vp, vp]
+    L.sb_ctx_stream.argtypes = [vp]
+    L.sb_ctx_stream.restype = vp
+    L.sb_ctx_sync.argtypes = [vp]
+    L.sb_ctx_device_name.argtypes = [vp, C.c_char_p, sz]
+    L.sb_ctx_sm_count.argtypes = [vp]
+    L.sb_ctx_launch_count.argtypes = [vp]
+    L.sb_ctx_launch_count.restype = u64
+    L.sb_workspace_bytes.argtypes = [i, i, sz]
+    L.sb_workspace_bytes.restype = sz
+    L.sb_timer_begin.argtypes = [vp]
+    L.sb_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
+    L.sb_malloc.argtypes = [vp, C.POINTER(vp), sz]
+    L.sb_free.argtypes = [vp, vp]
+    L.sb_host_alloc.argtypes = [vp, C.POINTER(vp), sz]
+    L.sb_host_free.argtypes = [vp, vp]
+    L.sb_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    L.sb_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    L.sb_memset.argtypes = [vp, vp, i, sz]
+    for t in DTYPES:
+        getattr(L, f"sb_iota_{t}").argtypes = [vp, vp, sz, u64]
+        getattr(L, f"sb_segreduce_{t}").argtypes = [vp, vp, sz, sz]
+    for t in DTYPES[1:]:
+        getattr(L, f"sb_reduce_{t}").argtypes = [vp, vp, sz, vp]
+        getattr(L, f"sb_scan_{t}").argtypes = [vp, vp, vp, sz, i, sz, vp]
+        getattr(L, f"sb_segscan_{t}").argtypes = [vp, vp, vp, sz, sz, vp, i]
+        getattr(L, f"sb_carry_add_{t}").argtypes = [vp, vp, sz, vp]
+        getattr(L, f"sb_exclusive_carry_{t}").argtypes = [vp, vp, i, vp]
+    for t in ("i32", "i64"):
+        getattr(L, f"sb_check_iota_{t}").argtypes = [vp, vp, sz, u64, i, sz, vp]
+    L.sb_host_reduce.argtypes = [vp, i, vp, sz, vp]
+    L.sb_host_scan.argtypes = [vp, i, vp, vp, sz, i, sz]
+    L.sb_host_segreduce.argtypes = [vp, i, vp, sz, sz]
+    L.sb_host_segscan.argtypes = [vp, i, vp, vp, sz, sz, vp, i]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise SbError(rc, lib().sb_strerror(rc).decode())
+
+
+def _ptr(x) -> Optional[int]:
+    if x is None:
+        return None
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):  # numpy
+        return x.ctypes.data
+    return int(x)
+
+
+def dtype_of(x) -> str:
+    """Map a torch / numpy dtype to the C-ABI suffix."""
+    name = str(getattr(x, "dtype", x)).replace("torch.", "")
+    table = {"int16": "i16", "int32": "i32", "int64": "i64", "float32": "f32", "float64": "f64"}
+    if name not in table:
+        raise TypeError(f"unsupported dtype {name}")
+    return table[name]
+
+
+class Context:
+    """One (device, stream) pair — the counterpart of the reference's BenchmarkArgs::device_queue
+    (/root/reference/include/command_line.h:129-140).  Methods take torch tensors (or raw device
+    addresses) and forward to the C ABI; they are asynchronous on the ctx stream."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._h = C.c_void_p()
+        _check(lib().sb_ctx_create(device, stream, C.byref(self._h)))
+        self.device = device
+
+    def close(self) -> None:
+        if self._h:
+            lib().sb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing
+    def sync(self) -> None:
+        _check(lib().sb_ctx_sync(self._h))
+
+    def set_stream(self, stream: Optional[int]) -> None:
+        _check(lib().sb_ctx_set_stream(self._h, stream))
+
+    @property
+    def stream(self) -> int:
+        return lib().sb_ctx_stream(self._h) or 0
+
+    @property
+    def launches(self) -> int:
+        return int(lib().sb_ctx_launch_count(self._h))
+
+    @property
+    def sm_count(self) -> int:
+        return int(lib().sb_ctx_sm_count(self._h))
+
+    def device_name(self) -> str:
+        buf = C.create_string_buffer(256)
+        _check(lib().sb_ctx_device_name(self._h, buf, 256))
+        return buf.value.decode()
+
+    def timer_begin(self) -> None:
+        _check(lib().sb_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        _check(lib().sb_timer_end(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    # -- ops on device buffers
+    def iota(self, out, offset: int = 0, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(out)
+        n = out.numel() if n is None else n
+        _check(getattr(lib(), f"sb_iota_{t}")(self._h, _ptr(out), n, offset))
+        return out
+
+    def reduce(self, x, out, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(x)
+        n = x.numel() if n is None else n
+        _check(getattr(lib(), f"sb_reduce_{t}")(self._h, _ptr(x), n, _ptr(out)))
+        return out
+
+    def scan(self, x, out, exclusive: bool = False, group_len: int = 0, seed=None, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(x)
+        n = x.numel() if n is None else n
+        _check(getattr(lib(), f"sb_scan_{t}")(self._h, _ptr(x), _ptr(out), n, int(exclusive), group_len, _ptr(seed)))
+        return out
+
+    def segreduce(self, x, seg_len: int, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(x)
+        n = x.numel() if n is None else n
+        _check(getattr(lib(), f"sb_segreduce_{t}")(self._h, _ptr(x), n, seg_len))
+        return x
+
+    def segscan(self, x, out, seg_len: int = 0, head_flags=None, exclusive: bool = False, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(x)
+        n = x.numel() if n is None else n
+        _check(getattr(lib(), f"sb_segscan_{t}")(self._h, _ptr(x), _ptr(out), n, seg_len, _ptr(head_flags), int(exclusive)))
+        return out
+
+    def carry_add(self, x, carry, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(x)
+        n = x.numel() if n is None else n
+        _check(getattr(lib(), f"sb_carry_add_{t}")(self._h, _ptr(x), n, _ptr(carry)))
+        return x
+
+    def exclusive_carry(self, totals, rank: int, out, dtype: Optional[str] = None):
+        t = dtype or dtype_of(totals)
+        _check(getattr(lib(), f"sb_exclusive_carry_{t}")(self._h, _ptr(totals), rank, _ptr(out)))
+        return out
+
+    def check_iota(self, data, mismatches, offset: int = 0, kind: int = 0, seg_len: int = 0, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(data)
+        n = data.numel() if n is None else n
+        _check(getattr(lib(), f"sb_check_iota_{t}")(self._h, _ptr(data), n, offset, kind, seg_len, _ptr(mismatches)))
+        return mismatches
+
+    # -- host-buffer (end-to-end) calls; synchronous
+    def host_reduce(self, h_in, h_out, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(h_in)
+        n = _numel(h_in) if n is None else n
+        _check(lib().sb_host_reduce(self._h, _DTYPE_ENUM[t], _ptr(h_in), n, _ptr(h_out)))
+        return h_out
+
+    def host_scan(self, h_in, h_out, exclusive: bool = False, group_len: int = 0, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(h_in)
+        n = _numel(h_in) if n is None else n
+        _check(lib().sb_host_scan(self._h, _DTYPE_ENUM[t], _ptr(h_in), _ptr(h_out), n, int(exclusive), group_len))
+        return h_out
+
+    def host_segreduce(self, h_inout, seg_len: int, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(h_inout)
+        n = _numel(h_inout) if n is None else n
+        _check(lib().sb_host_segreduce(self._h, _DTYPE_ENUM[t], _ptr(h_inout), n, seg_len))
+        return h_inout
+
+    def host_segscan(self, h_in, h_out, seg_len: int = 0, head_flags=None, exclusive: bool = False, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(h_in)
+        n = _numel(h_in) if n is None else n
+        _check(lib().sb_host_segscan(self._h, _DTYPE_ENUM[t], _ptr(h_in), _ptr(h_out), n, seg_len, _ptr(head_flags), int(exclusive)))
+        return h_out
+
+
+def _numel(x) -> int:
+    if hasattr(x, "numel"):
+        return int(x.numel())
+    return int(x.size)

@@ -1,0 +1,449 @@
+"""GPU parity tests: libsb_cuda (through the C ABI) against the oracle on the same inputs.
+
+Bar (BASELINE.json north_star): integer types bit-exact; fp32 within 1e-5*log2(N), fp64 within
+1e-12*log2(N) relative.  Full BASELINE sizes are checked through closed forms of the iota input
+ evaluated on the device.
+"""
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TORCH = {"i16": torch.int16, "i32": torch.int32, "i64": torch.int64, "f32": torch.float32, "f64": torch.float64}
+FMT = {"i16": "<h", "i32": "<i", "i64": "<q", "f32": "<f", "f64": "<d"}
+ALL4 = ("i32", "i64", "f32", "f64")
+
+
+def tol(t, n):
+    return (1e-5 if t == "f32" else 1e-12) * max(np.log2(max(n, 2)), 1.0)
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def assert_close(t, got, want, n, what=""):
+    got = np.asarray(got)
+    want = np.asarray(want)
+    if t[0] == "i":
+        if not np.array_equal(got, want):
+            bad = np.flatnonzero(got != want)
+            raise AssertionError(f"{what} {t}: {bad.size} integer mismatches, first at {bad[:5]}: got {got[bad[:5]]} want {want[bad[:5]]}")
+    else:
+        g, w = got.astype(np.float64), want.astype(np.float64)
+        err = np.abs(g - w) / np.maximum(np.abs(w), 1.0)
+        assert err.max(initial=0.0) <= tol(t, n), f"{what} {t}: rel err {err.max()} > {tol(t, n)} at {err.argmax()}"
+
+
+def rand_input(t, n, seed=42):
+    rng = np.random.default_rng(seed)
+    if t[0] == "i":
+        return rng.integers(-(1 << 15), 1 << 15, size=n).astype({"i16": np.int16, "i32": np.int32, "i64": np.int64}[t])
+    return (rng.random(n) * 2 - 1).astype(np.float32 if t == "f32" else np.float64)
+
+
+# ---------------------------------------------------------------------------------------------- iota
+@pytest.mark.parametrize("t", ["i16", "i32", "i64", "f32", "f64"])
+@pytest.mark.parametrize("n,offset", [(1, 0), (1000, 0), (4099, 7), (1 << 16, (1 << 24) - 5), (1 << 12, (1 << 33) + 1)])
+def test_iota(ctx, O, t, n, offset):
+    x = torch.empty(n + 1, dtype=TORCH[t], device="cuda")[1:]  # not 16-byte aligned
+    ctx.iota(x, offset)
+    assert np.array_equal(x.cpu().numpy(), O.iota(t, n, offset))
+    y = torch.empty(n, dtype=TORCH[t], device="cuda")
+    ctx.iota(y, offset)
+    assert np.array_equal(y.cpu().numpy(), O.iota(t, n, offset))
+
+
+# ------------------------------------------------------------------------------------------- reduce
+@pytest.mark.parametrize("t", ALL4)
+@pytest.mark.parametrize("n", [0, 1, 3, 255, 256, 1000, 4097, 8192, (1 << 16) + 3, 1 << 20, (1 << 22) + 12345])
+def test_reduce_vs_oracle(ctx, O, t, n):
+    hx = O.iota(t, n)
+    out = torch.full((1,), 77, dtype=TORCH[t], device="cuda")
+    ctx.reduce(dev(hx) if n else torch.empty(0, dtype=TORCH[t], device="cuda"), out)
+    got = out.cpu().numpy()[0]
+    if n == 0:
+        assert got == 0
+        return
+    if t[0] == "i":
+        want = O.wrap(O.kat_reduce(n), t)
+        assert got == want
+        if n % 256 == 0:
+            assert got == O.reduce(t, hx, 256)  # the reference's own multi-pass tree
+    else:
+        want = O.reduce(t, hx, 256) if n % 256 == 0 else float(np.sum(hx.astype(np.float64)))
+        assert abs(float(got) - float(want)) <= tol(t, n) * abs(float(want))
+
+
+def test_reduce_golden_vectors(ctx, O, golden):
+    """libsb_cuda vs the values the unmodified reference produced (tests/golden)."""
+    done = 0
+    for g in golden["reduction"]:
+        if g["variant"] != "Hierarchical" or g["local"] & (g["local"] - 1) or g["size"] % g["local"]:
+            continue  # non-power-of-two --local / dropped tails are harness-level quirks
+        t, n = g["dtype"], g["size"]
+        x = torch.empty(n, dtype=TORCH[t], device="cuda")
+        ctx.iota(x)
+        out = torch.zeros(1, dtype=TORCH[t], device="cuda")
+        ctx.reduce(x, out)
+        got = out.cpu().numpy()[0]
+        if t[0] == "i":
+            assert struct.pack(FMT[t], got).hex() == g["result_hex"], g
+        else:
+            assert abs(float(got) - g["result"]) <= tol(t, n) * abs(g["result"]), g
+        done += 1
+    assert done >= 20
+
+
+def test_reduce_config1_bits(ctx):
+    """BASELINE config 1: int32, N = 16 777 216 -> 0xFF800000."""
+    x = torch.empty(1 << 24, dtype=torch.int32, device="cuda")
+    ctx.iota(x)
+    out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ctx.reduce(x, out)
+    assert out.item() == -8388608
+
+
+@pytest.mark.parametrize("t", ALL4)
+def test_reduce_random_unaligned_and_deterministic(ctx, t):
+    n = (1 << 21) + 77
+    hx = rand_input(t, n + 3)
+    x = dev(hx)
+    outs = []
+    for off in (0, 1, 3):
+        out = torch.zeros(1, dtype=TORCH[t], device="cuda")
+        ctx.reduce(x[off:off + n], out)
+        got = out.cpu().numpy()[0]
+        ref = hx[off:off + n]
+        if t[0] == "i":
+            assert got == ref.sum(dtype=ref.dtype)
+        else:
+            exact = float(np.sum(ref.astype(np.float64))) if t == "f32" else float(np.sum(ref.astype(np.longdouble)))
+            scale = float(np.sum(np.abs(ref.astype(np.float64))))
+            assert abs(float(got) - exact) <= tol(t, n) * scale
+        outs.append(got)
+    a = torch.zeros(1, dtype=TORCH[t], device="cuda")
+    b = torch.zeros(1, dtype=TORCH[t], device="cuda")
+    ctx.reduce(x[:n], a)
+    ctx.reduce(x[:n], b)
+    assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()  # fixed summation order
+
+
+# --------------------------------------------------------------------------------------------- scan
+SCAN_N = [1, 2, 31, 257, 4096, 4097, 12289, (1 << 16) + 1, (1 << 20) + 4099]
+
+
+@pytest.mark.parametrize("t", ALL4)
+@pytest.mark.parametrize("exclusive", [False, True])
+@pytest.mark.parametrize("n", SCAN_N)
+def test_scan_global_iota(ctx, O, t, exclusive, n):
+    hx = O.iota(t, n)
+    x = dev(hx)
+    y = torch.empty_like(x)
+    ctx.scan(x, y, exclusive=exclusive)
+    assert_close(t, y.cpu().numpy(), O.scan(t, hx, exclusive, 0), n, "scan")
+
+
+@pytest.mark.parametrize("t", ALL4)
+@pytest.mark.parametrize("group_len", [1, 2, 3, 64, 100, 256, 1024, 4096, 8192, 20000])
+@pytest.mark.parametrize("exclusive", [False, True])
+def test_scan_group_scope(ctx, O, t, group_len, exclusive):
+    n = 3 * 20000 + 4321
+    hx = rand_input(t, n)
+    x = dev(hx)
+    y = torch.empty_like(x)
+    ctx.scan(x, y, exclusive=exclusive, group_len=group_len)
+    assert_close(t, y.cpu().numpy(), O.scan(t, hx, exclusive, group_len), n, f"scan group={group_len}")
+
+
+@pytest.mark.parametrize("t", ALL4)
+def test_scan_in_place_unaligned_seed(ctx, O, t):
+    n = (1 << 18) + 5
+    hx = rand_input(t, n + 1)
+    x = dev(hx)[1:]  # misaligned for 16-byte vectors
+    y = torch.empty(n + 1, dtype=TORCH[t], device="cuda")[1:]
+    ctx.scan(x, y)
+    want = O.scan(t, hx[1:])
+    assert_close(t, y.cpu().numpy(), want, n, "unaligned")
+    z = dev(hx[1:])
+    ctx.scan(z, z, exclusive=True)  # in place
+    assert_close(t, z.cpu().numpy(), O.scan(t, hx[1:], True), n, "in place")
+    seed = dev(np.array([5], dtype=hx.dtype))
+    z = dev(hx[1:])
+    out = torch.empty_like(z)
+    ctx.scan(z, out, seed=seed)
+    if t[0] == "i":
+        assert np.array_equal(out.cpu().numpy(), want + hx.dtype.type(5))
+    else:
+        assert_close(t, out.cpu().numpy(), want.astype(np.float64) + 5.0, n, "seed")
+
+
+def test_scan_many_launches_mixed_types(ctx, O):
+    """Descriptors are reused without a reset (epoch-tagged); tickets are never rewound."""
+    n = (1 << 17) + 11
+    for it in range(40):
+        t = ALL4[it % 4]
+        hx = rand_input(t, n, seed=it)
+        x = dev(hx)
+        y = torch.empty_like(x)
+        ctx.scan(x, y, exclusive=bool(it & 1))
+        assert_close(t, y.cpu().numpy(), O.scan(t, hx, bool(it & 1)), n, f"launch {it}")
+
+
+# ------------------------------------------------------------------------------------------ segscan
+@pytest.mark.parametrize("t", ALL4)
+@pytest.mark.parametrize("seg_len", [1, 7, 64, 256, 1024, 4096, 16384, 50000])
+@pytest.mark.parametrize("exclusive", [False, True])
+def test_segscan_implicit_heads(ctx, O, t, seg_len, exclusive):
+    n = 150000
+    hx = O.iota(t, n)
+    x = dev(hx)
+    y = torch.empty_like(x)
+    ctx.segscan(x, y, seg_len=seg_len, exclusive=exclusive)
+    assert_close(t, y.cpu().numpy(), O.scan(t, hx, exclusive, seg_len), n, f"segscan L={seg_len}")
+
+
+@pytest.mark.parametrize("t", ALL4)
+@pytest.mark.parametrize("density", [0.0, 1e-5, 1e-3, 0.05, 0.5, 1.0])
+@pytest.mark.parametrize("exclusive", [False, True])
+def test_segscan_explicit_flags(ctx, O, t, density, exclusive):
+    n = (1 << 18) + 333
+    rng = np.random.default_rng(int(density * 1e6) + 1)
+    flags = (rng.random(n) < density).astype(np.uint8)
+    hx = rand_input(t, n)
+    x, f = dev(hx), dev(flags)
+    y = torch.empty_like(x)
+    ctx.segscan(x, y, head_flags=f, exclusive=exclusive)
+    assert_close(t, y.cpu().numpy(), O.scan(t, hx, exclusive, 0, flags), n, f"flags d={density}")
+    # unaligned flag / data pointers
+    y2 = torch.empty(n, dtype=TORCH[t], device="cuda")
+    ctx.segscan(x[1:], y2[1:], head_flags=f[1:], exclusive=exclusive, n=n - 1)
+    assert_close(t, y2[1:].cpu().numpy(), O.scan(t, hx[1:], exclusive, 0, flags[1:]), n, "flags unaligned")
+
+
+# ---------------------------------------------------------------------------------------- segreduce
+@pytest.mark.parametrize("t", ["i16", "i32", "i64", "f32", "f64"])
+@pytest.mark.parametrize("L", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 16384, 6, 100, 1000])
+def test_segreduce_vs_oracle(ctx, O, t, L):
+    n = L * max(3, 70000 // L)
+    hx = O.iota(t, n)
+    x = dev(hx)
+    ctx.segreduce(x, L)
+    assert_close(t, x.cpu().numpy(), O.segreduce(t, hx, L), n, f"segreduce L={L}")
+
+
+@pytest.mark.parametrize("t", ["i16", "i32", "i64", "f32", "f64"])
+def test_segreduce_random_and_unaligned(ctx, O, t):
+    L, n = 256, 256 * 999
+    hx = rand_input(t, n + 1)
+    x = dev(hx)[1:]
+    ctx.segreduce(x, L)
+    assert_close(t, x.cpu().numpy(), O.segreduce(t, hx[1:], L), n, "unaligned")
+    x = dev(hx[:n])
+    ctx.segreduce(x, L)
+    assert_close(t, x.cpu().numpy(), O.segreduce(t, hx[:n], L), n, "random")
+
+
+def test_segreduce_golden_vectors(ctx, golden):
+    import hashlib
+
+    done = 0
+    for g in golden["segmentedreduction"]:
+        if g["variant"] != "Hierarchical" or g["dtype"] == "f32" or g["size"] > (1 << 22):
+            continue  # fp32: tree order differs (tolerance, tested above); ints / fp64-on-iota are exact
+        t, n, L = g["dtype"], g["size"], g["local"]
+        x = torch.empty(n, dtype=TORCH[t], device="cuda")
+        ctx.iota(x)
+        ctx.segreduce(x, L)
+        assert hashlib.sha256(x.cpu().numpy().tobytes()).hexdigest() == g["sha256"], g
+        done += 1
+    assert done >= 25
+
+
+# ------------------------------------------------------------------------------------------- errors
+def test_error_codes(ctx, pkg):
+    x = torch.zeros(1024, dtype=torch.int32, device="cuda")
+    with pytest.raises(pkg.SbError) as e:
+        ctx.segreduce(x, 0)
+    assert e.value.status == -4
+    with pytest.raises(pkg.SbError) as e:
+        ctx.segreduce(x, 100)  # 1024 % 100 != 0 — the reference asserts this (segmentedreduction.cpp:23)
+    assert e.value.status == -4
+    with pytest.raises(pkg.SbError) as e:
+        ctx.segscan(x, x, seg_len=0)
+    assert e.value.status == -4
+    with pytest.raises(pkg.SbError) as e:
+        ctx.reduce(x.data_ptr() + 2, x, n=10, dtype="i32")
+    assert e.value.status == -2
+    with pytest.raises(pkg.SbError) as e:
+        ctx.reduce(x, None)
+    assert e.value.status == -1
+
+
+# ---------------------------------------------------------------------------- multi-GPU building blocks
+@pytest.mark.parametrize("t", ALL4)
+def test_carry_add_and_exclusive_carry(ctx, O, t):
+    n = (1 << 16) + 3
+    hx = rand_input(t, n)
+    totals = dev(np.array([3, 5, 7, 11], dtype=hx.dtype))
+    carry = torch.zeros(1, dtype=TORCH[t], device="cuda")
+    ctx.exclusive_carry(totals, 3, carry)
+    assert carry.item() == 15
+    ctx.exclusive_carry(totals, 0, carry)
+    assert carry.item() == 0
+    ctx.exclusive_carry(totals, 2, carry)
+    x = dev(hx)
+    ctx.carry_add(x, carry)
+    assert np.array_equal(x.cpu().numpy(), hx + hx.dtype.type(8))
+    x = dev(hx)[1:]
+    ctx.carry_add(x, carry)
+    assert np.array_equal(x.cpu().numpy(), hx[1:] + hx.dtype.type(8))
+
+
+@pytest.mark.parametrize("t", ["i32", "i64"])
+def test_sharded_scan_equals_global(ctx, O, t):
+    """The N>1 data path on one GPU: P shards, local scan, totals exchange, carry — two strategies."""
+    P, S = 4, (1 << 16) + 64
+    n = P * S
+    full = torch.empty(n, dtype=TORCH[t], device="cuda")
+    ctx.iota(full)
+    want = O.scan(t, O.iota(t, n))
+    # (a) scan -> all-gather totals -> carry-add  (north-star design)
+    out = torch.empty_like(full)
+    totals = torch.zeros(P, dtype=TORCH[t], device="cuda")
+    for r in range(P):
+        ctx.scan(full[r * S:(r + 1) * S], out[r * S:(r + 1) * S])
+        totals[r] = out[(r + 1) * S - 1]
+    carry = torch.zeros(1, dtype=TORCH[t], device="cuda")
+    for r in range(P):
+        ctx.exclusive_carry(totals, r, carry)
+        ctx.carry_add(out[r * S:(r + 1) * S], carry)
+    assert np.array_equal(out.cpu().numpy(), want)
+    # (b) reduce -> all-gather totals -> seeded scan  (3 instead of 4 passes over the shard)
+    out2 = torch.empty_like(full)
+    for r in range(P):
+        ctx.reduce(full[r * S:(r + 1) * S], totals[r:r + 1])
+    for r in range(P):
+        ctx.exclusive_carry(totals, r, carry)
+        ctx.scan(full[r * S:(r + 1) * S], out2[r * S:(r + 1) * S], seed=carry)
+        ctx.sync()
+    assert np.array_equal(out2.cpu().numpy(), want)
+
+
+# ------------------------------------------------------------------------------- host-buffer entry points
+@pytest.mark.parametrize("t", ALL4)
+def test_host_api(ctx, O, t):
+    n, L = (1 << 18), 256
+    hx = O.iota(t, n)
+    out = np.zeros(1, dtype=hx.dtype)
+    ctx.host_reduce(hx, out)
+    want = O.reduce(t, hx, L)
+    if t[0] == "i":
+        assert out[0] == want
+    else:
+        assert abs(float(out[0]) - float(want)) <= tol(t, n) * abs(float(want))
+    res = np.empty_like(hx)
+    ctx.host_scan(hx, res)
+    assert_close(t, res, O.scan(t, hx), n, "host_scan")
+    ctx.host_scan(hx, res, exclusive=True, group_len=L)
+    assert_close(t, res, O.scan(t, hx, True, L), n, "host_scan group")
+    buf = hx.copy()
+    ctx.host_segreduce(buf, L)
+    assert_close(t, buf, O.segreduce(t, hx, L), n, "host_segreduce")
+    flags = (np.arange(n) % 1000 == 0).astype(np.uint8)
+    ctx.host_segscan(hx, res, head_flags=flags)
+    assert_close(t, res, O.scan(t, hx, False, 0, flags), n, "host_segscan")
+
+
+# ----------------------------------------------------------------- BASELINE sizes via closed forms (A.4)
+def _mismatches(ctx, data, **kw):
+    m = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ctx.check_iota(data, m, **kw)
+    return int(m.item())
+
+
+def test_check_kernel_detects_errors(ctx):
+    n = 1 << 20
+    x = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.iota(x)
+    y = torch.empty_like(x)
+    ctx.scan(x, y)
+    assert _mismatches(ctx, y, kind=0) == 0
+    assert _mismatches(ctx, y, kind=1) == n - 1  # wrong kind: only y[0] = 0 matches
+    y[12345] += 1
+    assert _mismatches(ctx, y, kind=0) == 1
+
+
+def test_config3_scan_and_segscan_int32_2p30(ctx):
+    """BASELINE config 3: scan + segmentedscan, int32, N = 2^30, segment / work-group length 256."""
+    n = 1 << 30
+    x = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.iota(x)
+    y = torch.empty_like(x)
+    ctx.scan(x, y, exclusive=True)  # global, decoupled look-back
+    assert _mismatches(ctx, y, kind=1) == 0
+    ctx.scan(x, y, exclusive=True, group_len=256)  # work-group scope
+    assert _mismatches(ctx, y, kind=1, seg_len=256) == 0
+    ctx.segscan(x, y, seg_len=256)
+    assert _mismatches(ctx, y, kind=0, seg_len=256) == 0
+    flags = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    flags[::256] = 1
+    y.zero_()
+    ctx.segscan(x, y, head_flags=flags)  # explicit head flags: look-back over (value, flag) pairs
+    assert _mismatches(ctx, y, kind=0, seg_len=256) == 0
+    flags.zero_()
+    flags[::65536] = 1
+    ctx.segscan(x, y, head_flags=flags, exclusive=True)
+    assert _mismatches(ctx, y, kind=1, seg_len=65536) == 0
+
+
+def test_config2_prefixsum_and_reduction_2p28(ctx, O):
+    """BASELINE config 2: reduction + prefixsum, fp32 and int64, N = 2^28."""
+    n = 1 << 28
+    x = torch.empty(n, dtype=torch.int64, device="cuda")
+    ctx.iota(x)
+    out = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ctx.reduce(x, out)
+    assert out.item() == 36028796884746240
+    y = torch.empty_like(x)
+    ctx.scan(x, y)
+    assert _mismatches(ctx, y, kind=0) == 0
+    del x, y
+    xf = torch.empty(n, dtype=torch.float32, device="cuda")
+    ctx.iota(xf)
+    outf = torch.zeros(1, dtype=torch.float32, device="cuda")
+    ctx.reduce(xf, outf)
+    ref_tree = 36028797018963968.0  # the reference's fp32 tree result (2^55), SURVEY.md A.4
+    assert abs(outf.item() - ref_tree) <= tol("f32", n) * ref_tree
+    yf = torch.empty_like(xf)
+    ctx.scan(xf, yf)
+    # fp32 prefix sum vs the exact real-number prefix sum of the (rounded) fp32 inputs, sampled
+    idx = torch.tensor([0, 1, 1000, (1 << 24) + 1, (1 << 27) + 12345, n - 1], device="cuda")
+    exact = torch.cumsum(xf[: (1 << 20)].double(), 0)
+    assert torch.allclose(yf[: (1 << 20)].double(), exact, rtol=tol("f32", n), atol=0)
+    got = yf[idx].double().cpu().numpy()
+    want = np.array([float(O.kat_scan(int(i), False)) for i in idx.cpu().numpy()])
+    assert np.all(np.abs(got - want) <= tol("f32", n) * np.maximum(want, 1.0))
+
+
+@pytest.mark.parametrize("L", [64, 128, 256, 512, 1024])
+def test_config4_segreduce_fp64_2p29(ctx, L):
+    """BASELINE config 4: segmentedreduction fp64, N = 2^29, --local sweep 64..1024.  All partial
+    sums are integers below 2^53, so fp64 is exact for any summation order."""
+    n = 1 << 29
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    ctx.iota(x)
+    ctx.segreduce(x, L)
+    heads = x[::L]
+    q = torch.arange(n // L, dtype=torch.float64, device="cuda")
+    assert torch.equal(heads, q * float(L * L) + float(L * (L - 1) // 2))
+    # everything that is not a head is untouched (pattern/segmentedreduction.cpp:116-118)
+    v = x.view(-1, L)[:, 1:]
+    base = (q * float(L)).unsqueeze(1)
+    off = torch.arange(1, L, dtype=torch.float64, device="cuda").unsqueeze(0)
+    step = 1 << 16
+    for s in range(0, v.shape[0], step):
+        assert torch.equal(v[s:s + step], base[s:s + step] + off)
