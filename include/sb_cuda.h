@@ -37,6 +37,7 @@ extern "C" {
 #define SB_VERSION 100 /* 0.1.0 */
 
 typedef struct sb_ctx sb_ctx;
+#define SB_STREAM_OWNED ((void*)(intptr_t)-1)
 
 enum sb_status {
   SB_OK = 0,
@@ -61,8 +62,9 @@ const char* sb_strerror(int status);
 int sb_device_count(int* count);
 
 /* One ctx per (device, stream): the counterpart of `BenchmarkArgs::device_queue`
- * (include/command_line.h:133,152-154).  `stream` is a cudaStream_t (NULL = a new non-blocking
- * stream owned by the ctx).  The ctx owns the scratch the kernels need (block partials, tile
+ * (include/command_line.h:133,152-154).  `stream` is a cudaStream_t: NULL is the CUDA default
+ * stream (as in every CUDA API), SB_STREAM_OWNED asks for a new non-blocking stream owned by the
+ * ctx (the in-order queue of include/command_line.h:154).  The ctx owns the scratch the kernels need (block partials, tile
  * descriptors, tickets), sized once for the device, so that op calls never allocate. */
 int sb_ctx_create(int device, void* stream, sb_ctx** out);
 int sb_ctx_destroy(sb_ctx* ctx);

@@ -57,7 +57,7 @@ int sb_ctx_create(int device, void* stream, sb_ctx** out) {
   if(!ctx) return SB_ERR_WORKSPACE;
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  if(stream) {
+  if(stream != SB_STREAM_OWNED) {
     ctx->stream = (cudaStream_t)stream;
   } else {
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -86,7 +86,7 @@ int sb_ctx_create(int device, void* stream, sb_ctx** out) {
 int sb_ctx_destroy(sb_ctx* ctx) {
   if(!ctx) return SB_OK;
   sb_device_guard guard(ctx->device);
-  if(ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->partials);
   cudaFree(ctx->reduce_ticket);
   cudaFree(ctx->scan_ticket);
@@ -111,7 +111,7 @@ int sb_ctx_set_stream(sb_ctx* ctx, void* stream) {
     cudaStreamDestroy(ctx->stream);
     ctx->own_stream = false;
   }
-  if(stream) {
+  if(stream != SB_STREAM_OWNED) {
     ctx->stream = (cudaStream_t)stream;
   } else {
     SB_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

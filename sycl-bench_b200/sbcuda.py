@@ -124,7 +124,11 @@ class Context:
     (/root/reference/include/command_line.h:129-140).  Methods take torch tensors (or raw device
     addresses) and forward to the C ABI; they are asynchronous on the ctx stream."""
 
+    OWNED_STREAM = C.c_void_p(-1).value  # SB_STREAM_OWNED
+
     def __init__(self, device: int = 0, stream: Optional[int] = None):
+        """stream: a cudaStream_t handle as int (0 / None = the CUDA default stream, which is what
+        torch.cuda.current_stream().cuda_stream is by default); Context.OWNED_STREAM = new stream."""
         self._h = C.c_void_p()
         _check(lib().sb_ctx_create(device, stream, C.byref(self._h)))
         self.device = device
