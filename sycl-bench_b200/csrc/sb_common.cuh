@@ -137,3 +137,4 @@ inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintp
 // workspace growth helpers (sb_ctx.cu)
 int sb_ctx_reserve_desc(sb_ctx* ctx, size_t count64, size_t count128);
 int sb_ctx_reserve_stage(sb_ctx* ctx, int which, size_t bytes);
+size_t sb_scan_tile_bytes();  // sb_scan.cu

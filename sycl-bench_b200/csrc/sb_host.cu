@@ -122,7 +122,7 @@ size_t sb_workspace_bytes(int op, int dtype, size_t n) {
   case SB_OP_REDUCE: return 148 * 32 * 8 + 256;  // block partials + ticket
   case SB_OP_SCAN:
   case SB_OP_SEGSCAN: {
-    const size_t tile = 16384 / s;  // 16 KB tiles
+    const size_t tile = sb_scan_tile_bytes() / s;
     const size_t tiles = (n + tile - 1) / tile;
     return tiles * (s == 4 ? 8 : 16) + 256;
   }

@@ -7,36 +7,90 @@
 // pattern/segmentedreduction.cpp:35-61).
 //
 // B200 design: HBM-bound copy-like stream (algorithmic bytes 2*N*s).
-//  - one CTA of 256 threads per 16 KB tile; a warp owns K=4 consecutive rows of 32 x 16 B, all
-//    128-bit loads are issued before the first add (64 B in flight per thread, ~80 KB per SM).
-//  - tile ids come from an atomic ticket (forward progress does not depend on CTA dispatch order).
-//  - tile descriptors {status, value} are written/read with ONE relaxed 64-bit (4-byte T) or
-//    128-bit (8-byte T, st/ld .b128) access, so no fence separates flag and value.
-//  - status carries a per-launch epoch: descriptors are never reset between launches.
-//  - the segmented variants run the same kernel on (value, head-flag) pairs:
-//    (v1,f1)(+)(v2,f2) = (f2 ? v2 : v1+v2, f1|f2).  A tile that contains a head publishes its
-//    INCLUSIVE state immediately (it does not depend on its predecessors); a tile that starts on
-//    a head skips the look-back; if every tile starts on a head (power-of-two segment <= tile)
-//    neither tickets nor descriptors are touched.
+//
+//  scan_ws_kernel (16-byte aligned buffers) — persistent, warp-specialised, mbarrier-only:
+//    * grid = co-resident CTAs (sm_count x occupancy), tiles dealt round-robin: tile = r*G + pos.
+//    * producer warp: keeps a ring of WS_STAGES cp.async.bulk (TMA) tile loads in flight
+//      (full/empty mbarriers, complete_tx byte counting).
+//    * worker warps, software-pipelined over the CTA's tiles with depth WS_DEPTH:
+//        phase A (tile k+D): read the tile from the ring, reduce it to one (sum, has-head) pair per
+//                            warp, hand the pairs to the look-back warp (agg mbarrier);
+//        phase B (tile k)  : wait for the tile prefix (prefix mbarrier), read the tile again from
+//                            the ring, scan it with the carry and write 128-bit coalesced stores
+//                            straight from registers, then release the stage (empty mbarrier).
+//    * look-back warp: combines the warp pairs, publishes the tile descriptor, runs the ROUND
+//      look-back (below) and posts the tile prefix.  Workers never wait for a look-back that has not
+//      had D tiles of time to finish; there is no __syncthreads after the prologue.
+//    History (profiles/): v1 one CTA per 16 KB tile + LDG: 2.1 TB/s, 40 barrier-stall cycles per
+//    issue, memory duty ~25 % (ncu).  v2 persistent + TMA ring, block barriers: 2.7-3.3 TB/s,
+//    5.5 TB/s without look-back.  v3 + round look-back: 2.9-4.2 TB/s.
+//
+//  Round look-back: the G tiles of a round are in flight together and publish their aggregates at
+//    about the same time, so a tile sums the aggregates of positions pos-1..0 of ITS OWN round
+//    (SCAN_WINDOW x 32 descriptors per step, all loads issued before the first wait; a tile that
+//    contains a segment head ends the walk) and adds the previous round's prefix, which the CTA
+//    at position G-1 publishes once per round.  One dependent step per ROUND instead of one per
+//    32 tiles, nobody waits for a neighbour's look-back, and the summation order is fixed
+//    (deterministic floating point).
+//
+//  scan_kernel (unaligned or tiny inputs): one CTA per 16 KB tile, tile ids from an atomic ticket,
+//    classic windowed look-back.
+//
+//  Common: a warp owns K consecutive rows of 32 x 16 B; per row one warp (segmented) scan by
+//  shuffles.  Descriptors {status, value} are written/read with ONE relaxed 64-bit (4-byte T) or
+//  128-bit (8-byte T, st/ld .b128) access, so no fence separates flag and value; the status
+//  carries a per-launch epoch, so descriptors are never reset between launches.  Segmented
+//  variants run the same code on (value, head-flag) pairs: (v1,f1)(+)(v2,f2) = (f2 ? v2 : v1+v2,
+//  f1|f2); if every tile starts on a head (power-of-two segment <= tile) no descriptor is touched.
 #include "sb_common.cuh"
 
 namespace {
 
-constexpr int SCAN_NT = 256;
-constexpr int SCAN_NW = SCAN_NT / 32;
-constexpr int SCAN_K = 4;
+// ---- tuning knobs (make tune builds variants with -D...) -------------------------------------------------
+#ifndef SB_SCAN_NT
+#define SB_SCAN_NT 256  // ticketed kernel: threads
+#endif
+#ifndef SB_SCAN_K
+#define SB_SCAN_K 4  // ticketed kernel: rows per warp
+#endif
+#ifndef SB_SCAN_WINDOW
+#define SB_SCAN_WINDOW 4  // look-back: batches of 32 descriptors polled per step
+#endif
+#ifndef SB_WS_NW
+#define SB_WS_NW 16  // persistent kernel: worker warps
+#endif
+#ifndef SB_WS_K
+#define SB_WS_K 8  // rows per worker warp and tile (tile = NW*K*512 bytes = 64 KB)
+#endif
+#ifndef SB_WS_STAGES
+#define SB_WS_STAGES 3
+#endif
+#ifndef SB_WS_DEPTH
+#define SB_WS_DEPTH 1  // phase A runs this many tiles ahead of phase B
+#endif
+#ifndef SB_WS_MINB
+#define SB_WS_MINB 1
+#endif
+constexpr int SCAN_NT = SB_SCAN_NT;
+constexpr int SCAN_K = SB_SCAN_K;
+constexpr int SCAN_WINDOW = SB_SCAN_WINDOW;
+constexpr int WS_NW = SB_WS_NW, WS_K = SB_WS_K, WS_STAGES = SB_WS_STAGES, WS_DEPTH = SB_WS_DEPTH;
+constexpr int WS_NSLOT = 2 * WS_DEPTH + 2;  // a fast warp is at most DEPTH+1 tiles ahead of a slow one
+constexpr int WS_THREADS = (WS_NW + 2) * 32;
 
 enum : uint32_t { ST_AGG = 1u, ST_INCL = 2u };
 enum { MODE_PLAIN = 0, MODE_IMPLICIT = 1, MODE_FLAGS = 2 };
 
-template <typename A> struct ScanCfg {
+template <typename A, int NW_, int K> struct TileCfg {
   static constexpr int VEC = 16 / sizeof(A);
-  static constexpr int ROW = 32 * VEC;
-  static constexpr int WCHUNK = SCAN_K * ROW;
-  static constexpr int TILE = SCAN_NW * WCHUNK;
+  static constexpr int NW = NW_;
+  static constexpr int ROW = 32 * VEC;      // elements one warp covers with one 128-bit access per lane
+  static constexpr int WCHUNK = K * ROW;    // consecutive elements owned by a warp
+  static constexpr int TILE = NW * WCHUNK;  // elements per tile
+  static constexpr int TILE_BYTES = NW * K * 512;
 };
 
-// ---- descriptors ---------------------------------------------------------------------------------
+// ---- descriptors ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t bits_of(uint32_t v) { return v; }
 __device__ __forceinline__ uint32_t bits_of(float v) { return __float_as_uint(v); }
 __device__ __forceinline__ unsigned long long bits_of(unsigned long long v) { return v; }
@@ -80,77 +134,141 @@ template <typename A> struct Desc<A, 8> {
   }
 };
 
-// decoupled look-back by one full warp: sum the aggregates of the predecessors down to the first
-// tile whose inclusive prefix is known.
+// classic decoupled look-back by one full warp: sum the aggregates of the predecessors down to the
+// first tile whose inclusive prefix is known (ticketed kernel)
 template <typename A>
 __device__ __forceinline__ A lookback(const typename Desc<A>::word* desc, long long tile, uint32_t epoch) {
   const int lane = sb::lane_id();
   A prefix = A(0);
   long long pred = tile - 1 - lane;
   for(;;) {
-    uint32_t st = (epoch << 2) | ST_INCL;
-    A val = A(0);
-    if(pred >= 0) {
-      do { Desc<A>::load(desc + pred, st, val); } while((st >> 2) != epoch);
+    uint32_t st[SCAN_WINDOW];
+    A val[SCAN_WINDOW];
+#pragma unroll
+    for(int w = 0; w < SCAN_WINDOW; ++w) {
+      st[w] = (epoch << 2) | ST_INCL;
+      val[w] = A(0);
+      if(pred - 32 * w >= 0) Desc<A>::load(desc + (pred - 32 * w), st[w], val[w]);
     }
-    const unsigned incl = __ballot_sync(SB_FULL_MASK, (st & 3u) == ST_INCL);
-    if(incl) {
-      const int first = __ffs(incl) - 1;
-      prefix += sb::warp_sum<A>(lane <= first ? val : A(0));
-      break;
+#pragma unroll
+    for(int w = 0; w < SCAN_WINDOW; ++w) {
+      if(pred - 32 * w >= 0) {
+        while((st[w] >> 2) != epoch) Desc<A>::load(desc + (pred - 32 * w), st[w], val[w]);
+      }
+      const unsigned incl = __ballot_sync(SB_FULL_MASK, (st[w] & 3u) == ST_INCL);
+      if(incl) {
+        const int first = __ffs(incl) - 1;
+        prefix += sb::warp_sum<A>(lane <= first ? val[w] : A(0));
+        return prefix;
+      }
+      prefix += sb::warp_sum<A>(val[w]);
     }
-    prefix += sb::warp_sum<A>(val);
-    pred -= 32;
+    pred -= 32 * SCAN_WINDOW;
   }
-  return prefix;
 }
 
-template <typename A, int MODE, bool ALIGNED>
-__global__ void __launch_bounds__(SCAN_NT)
-scan_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
-    const A* __restrict__ seed, typename Desc<A>::word* desc, unsigned long long* ticket, unsigned long long ticket_base,
-    uint32_t epoch, int use_lookback) {
-  using C = ScanCfg<A>;
-  constexpr int VEC = C::VEC;
-  constexpr int K = SCAN_K;
-  __shared__ long long s_tile;
-  __shared__ A s_wagg[SCAN_NW];
-  __shared__ int s_wflag[SCAN_NW];
-  __shared__ A s_prefix;
+// round look-back (persistent kernel), see the header comment
+template <typename A, int MODE>
+__device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, const typename Desc<A>::word* rdesc, long long tile,
+    long long G, uint32_t epoch, const A* __restrict__ seed) {
+  constexpr int U = SCAN_WINDOW;
+  const int lane = sb::lane_id();
+  const long long r = tile / G;
+  const int pos = (int)(tile - r * G);
+  const typename Desc<A>::word* row = desc + r * G;
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  long long tile;
-  if(use_lookback) {
-    if(threadIdx.x == 0) s_tile = (long long)(atomicAdd(ticket, 1ull) - ticket_base);
-    __syncthreads();
-    tile = s_tile;
-  } else {
-    tile = blockIdx.x;
+  // previous round's prefix: start the load now, look at it last
+  uint32_t rst = (epoch << 2) | ST_INCL;
+  A rval = A(0);
+  if(lane == 0) {
+    if(r > 0) Desc<A>::load(rdesc + (r - 1), rst, rval);
+    else if(MODE == MODE_PLAIN && seed) rval = *seed;
   }
-  const size_t base = (size_t)tile * C::TILE;
-  const size_t wbase = base + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
 
-  // ---- load -------------------------------------------------------------------------------------
-  A v[K][VEC];
-  unsigned hf[K];
-  const bool full_tile = base + C::TILE <= n;
+  A lane_sum = A(0);
+  bool head_found = false;
+  for(int hi = pos; hi > 0 && !head_found; hi -= 32 * U) {
+    uint32_t st[U];
+    A val[U];
+#pragma unroll
+    for(int u = 0; u < U; ++u) {
+      const int q = hi - 1 - (u * 32 + lane);
+      st[u] = (epoch << 2) | ST_AGG;
+      val[u] = A(0);
+      if(q >= 0) Desc<A>::load(row + q, st[u], val[u]);
+    }
+#pragma unroll
+    for(int u = 0; u < U; ++u) {
+      if(head_found) break;
+      const int q = hi - 1 - (u * 32 + lane);
+      if(q >= 0) {
+        while((st[u] >> 2) != epoch) Desc<A>::load(row + q, st[u], val[u]);
+      }
+      if(MODE != MODE_PLAIN) {
+        const unsigned heads = __ballot_sync(SB_FULL_MASK, (st[u] & 3u) == ST_INCL);
+        if(heads) {
+          const int first = __ffs(heads) - 1;  // lowest lane = nearest predecessor with a head
+          if(lane <= first) lane_sum += val[u];
+          head_found = true;
+          continue;
+        }
+      }
+      lane_sum += val[u];
+    }
+  }
+  A total = sb::warp_sum<A>(lane_sum);
+  if(!head_found) {
+    if(lane == 0 && r > 0) {
+      while((rst >> 2) != epoch) Desc<A>::load(rdesc + (r - 1), rst, rval);
+    }
+    total += sb::shfl_idx(rval, 0);
+  }
+  return total;
+}
+
+// ---- mbarrier / TMA bulk-copy primitives ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while(!done) {
+    asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---- per-warp building blocks ---------------------------------------------------------------------------------
+// head flags of the K x VEC elements a thread owns (bit c of hf[j] = element c of row j is a head)
+template <typename A, int MODE, int K>
+__device__ __forceinline__ void tile_head_flags(unsigned (&hf)[K], size_t wbase, size_t n, size_t seg_len, size_t seg_mask,
+    const uint8_t* __restrict__ flags) {
+  constexpr int VEC = 16 / sizeof(A);
+  constexpr int ROW = 32 * VEC;
 #pragma unroll
   for(int j = 0; j < K; ++j) {
-    const size_t idx = wbase + (size_t)j * C::ROW;
-    if(ALIGNED && (full_tile || idx + VEC <= n)) {
-      sb::Vec<A> t = sb::ldg_stream<A>(in + idx);
-#pragma unroll
-      for(int c = 0; c < VEC; ++c) v[j][c] = t.v[c];
-    } else {
-#pragma unroll
-      for(int c = 0; c < VEC; ++c) v[j][c] = (idx + c < n) ? in[idx + c] : A(0);
-    }
+    const size_t idx = wbase + (size_t)j * ROW;
     hf[j] = 0;
     if(MODE == MODE_IMPLICIT) {
       if(seg_mask != ~(size_t)0) {
+        if(seg_mask >= (size_t)(VEC - 1)) {
+          // power-of-two segment of at least one vector: only element 0 of an aligned vector can be a head
+          hf[j] = (idx & seg_mask) == 0 ? 1u : 0u;
+        } else {
 #pragma unroll
-        for(int c = 0; c < VEC; ++c) hf[j] |= (((idx + c) & seg_mask) == 0 ? 1u : 0u) << c;
+          for(int c = 0; c < VEC; ++c) hf[j] |= (((idx + c) & seg_mask) == 0 ? 1u : 0u) << c;
+        }
       } else {
         size_t r = idx % seg_len;
 #pragma unroll
@@ -160,15 +278,106 @@ scan_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t
         }
       }
     } else if(MODE == MODE_FLAGS) {
+      if(idx + VEC <= n && (reinterpret_cast<uintptr_t>(flags + idx) & (VEC - 1)) == 0) {
+        uint32_t w;  // VEC flag bytes in one access
+        if(VEC == 4) w = __ldg(reinterpret_cast<const uint32_t*>(flags + idx));
+        else w = __ldg(reinterpret_cast<const uint16_t*>(flags + idx));
 #pragma unroll
-      for(int c = 0; c < VEC; ++c) hf[j] |= ((idx + c < n && flags[idx + c]) ? 1u : 0u) << c;
+        for(int c = 0; c < VEC; ++c) hf[j] |= (((w >> (8 * c)) & 0xffu) ? 1u : 0u) << c;
+      } else {
+#pragma unroll
+        for(int c = 0; c < VEC; ++c) hf[j] |= ((idx + c < n && flags[idx + c]) ? 1u : 0u) << c;
+      }
       if(idx == 0) hf[j] |= 1u;
     }
   }
+}
 
-  // ---- pass 1: thread partials -> warp segmented scan per row -> warp aggregate --------------------
-  A carry_in[K];
-  bool open[K];
+// guarded global -> register load of a (possibly partial, possibly unaligned) tile
+template <typename A, bool ALIGNED, int K>
+__device__ __forceinline__ void tile_load_global(A (&v)[K][16 / sizeof(A)], const A* in, size_t wbase, bool full_tile, size_t n) {
+  constexpr int VEC = 16 / sizeof(A);
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    const size_t idx = wbase + (size_t)j * (32 * VEC);
+    if(ALIGNED && (full_tile || idx + VEC <= n)) {
+      sb::Vec<A> t = sb::ldg_stream<A>(in + idx);
+#pragma unroll
+      for(int c = 0; c < VEC; ++c) v[j][c] = t.v[c];
+    } else {
+#pragma unroll
+      for(int c = 0; c < VEC; ++c) v[j][c] = (idx + c < n) ? in[idx + c] : A(0);
+    }
+  }
+}
+
+// shared-memory ring -> registers (the lane-consecutive 16-byte layout is bank-conflict free)
+template <typename A, int K>
+__device__ __forceinline__ void tile_load_smem(A (&v)[K][16 / sizeof(A)], const unsigned char* warp_rows) {
+  constexpr int VEC = 16 / sizeof(A);
+  const unsigned char* sp = warp_rows + (threadIdx.x & 31) * 16;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    const sb::Vec<A> t = *reinterpret_cast<const sb::Vec<A>*>(sp + (size_t)j * 512);
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) v[j][c] = t.v[c];
+  }
+}
+
+// the warp's K rows reduced to (sum since the last head, contains a head)
+template <typename A, int MODE, int K>
+__device__ __forceinline__ void warp_reduce_rows(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A& agg, bool& has_head) {
+  constexpr int VEC = 16 / sizeof(A);
+  const int lane = threadIdx.x & 31;
+  if(MODE == MODE_PLAIN) {
+    A s = A(0);
+#pragma unroll
+    for(int j = 0; j < K; ++j) {
+      A r = v[j][0];
+#pragma unroll
+      for(int c = 1; c < VEC; ++c) r += v[j][c];
+      s += r;
+    }
+    agg = sb::warp_sum<A>(s);
+    has_head = false;
+    return;
+  }
+  A run = A(0);
+  bool runf = false;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    A s = A(0);
+    bool f = false;
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) {
+      if((hf[j] >> c) & 1u) {
+        s = v[j][c];
+        f = true;
+      } else {
+        s += v[j][c];
+      }
+    }
+    const unsigned hm = __ballot_sync(SB_FULL_MASK, f);
+    if(hm) {
+      const int hl = 31 - __clz(hm);
+      run = sb::warp_sum<A>(lane >= hl ? s : A(0));
+      runf = true;
+    } else {
+      run += sb::warp_sum<A>(s);
+    }
+  }
+  agg = run;
+  has_head = runf;
+}
+
+// pass 1: thread partials -> per-row warp segmented scan.  carry_in[j] = running sum entering the
+// thread's part of row j, relative to the start of the warp chunk (or the last head inside it);
+// open[j] = no head between the start of the warp chunk and that point.
+template <typename A, int MODE, int K>
+__device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A (&carry_in)[K], bool (&open)[K],
+    A& warp_agg, bool& warp_has_head) {
+  constexpr int VEC = 16 / sizeof(A);
+  const int lane = threadIdx.x & 31;
   A row_carry = A(0);
   bool warp_open = true;
 #pragma unroll
@@ -205,32 +414,108 @@ scan_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t
     row_carry = sb::shfl_idx(inc, 31);
     if(MODE != MODE_PLAIN && hm) warp_open = false;
   }
-  if(lane == 0) {
-    s_wagg[warp] = row_carry;
-    s_wflag[warp] = warp_open ? 0 : 1;
-  }
-  __syncthreads();
+  warp_agg = row_carry;
+  warp_has_head = !warp_open;
+}
 
-  // ---- block level: prefix of the warps before mine, tile aggregate ---------------------------------
-  A run = A(0), my_prefix = A(0);
-  bool run_open = true, my_open = true;
+// pass 2: rescan with the known carry, 128-bit coalesced stores from registers
+template <typename A, int MODE, bool ALIGNED, int K>
+__device__ __forceinline__ void tile_pass2_store(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], const A (&carry_in)[K],
+    const bool (&open)[K], A warp_prefix, size_t wbase, bool full_tile, size_t n, A* out, int exclusive) {
+  constexpr int VEC = 16 / sizeof(A);
 #pragma unroll
-  for(int u = 0; u < SCAN_NW; ++u) {
+  for(int j = 0; j < K; ++j) {
+    const size_t idx = wbase + (size_t)j * (32 * VEC);
+    A r = carry_in[j] + (open[j] ? warp_prefix : A(0));
+    sb::Vec<A> o;
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) {
+      if(MODE != MODE_PLAIN && ((hf[j] >> c) & 1u)) r = A(0);
+      const A e = r;
+      r += v[j][c];
+      o.v[c] = exclusive ? e : r;
+    }
+    if(ALIGNED && (full_tile || idx + VEC <= n)) {
+      sb::stg_vec<A>(out + idx, o);
+    } else {
+#pragma unroll
+      for(int c = 0; c < VEC; ++c)
+        if(idx + c < n) out[idx + c] = o.v[c];
+    }
+  }
+}
+
+// prefix of the warps in front of `warp` inside a tile and the tile's own (aggregate, has-head)
+template <typename A, int MODE, int NW>
+__device__ __forceinline__ void combine_warps(const A* wagg, const int* wflag, int warp, A& my_prefix, bool& my_open, A& tile_agg,
+    bool& tile_has_head) {
+  A run = A(0);
+  bool run_open = true;
+  my_prefix = A(0);
+  my_open = true;
+#pragma unroll
+  for(int u = 0; u < NW; ++u) {
     if(u == warp) {
       my_prefix = run;
       my_open = run_open;
     }
-    if(MODE != MODE_PLAIN && s_wflag[u]) {
-      run = s_wagg[u];
+    if(MODE != MODE_PLAIN && wflag[u]) {
+      run = wagg[u];
       run_open = false;
     } else {
-      run += s_wagg[u];
+      run += wagg[u];
     }
   }
-  const A tile_agg = run;
-  const bool tile_has_head = !run_open;
+  tile_agg = run;
+  tile_has_head = !run_open;
+}
 
-  // ---- decoupled look-back (warp 0) ---------------------------------------------------------------
+// ---- kernel 1: one CTA per tile, tile id from an atomic ticket (unaligned buffers, small inputs) -------------
+template <typename A, int MODE, bool ALIGNED>
+__global__ void __launch_bounds__(SCAN_NT)
+scan_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
+    const A* __restrict__ seed, typename Desc<A>::word* desc, unsigned long long* ticket, unsigned long long ticket_base,
+    uint32_t epoch, int use_lookback) {
+  using C = TileCfg<A, SCAN_NT / 32, SCAN_K>;
+  constexpr int VEC = C::VEC;
+  constexpr int K = SCAN_K;
+  __shared__ long long s_tile;
+  __shared__ A s_wagg[C::NW];
+  __shared__ int s_wflag[C::NW];
+  __shared__ A s_prefix;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long tile;
+  if(use_lookback) {
+    if(threadIdx.x == 0) s_tile = (long long)(atomicAdd(ticket, 1ull) - ticket_base);
+    __syncthreads();
+    tile = s_tile;
+  } else {
+    tile = blockIdx.x;
+  }
+  const size_t base = (size_t)tile * C::TILE;
+  const size_t wbase = base + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
+  const bool full_tile = base + C::TILE <= n;
+
+  A v[K][VEC];
+  unsigned hf[K];
+  tile_load_global<A, ALIGNED, K>(v, in, wbase, full_tile, n);
+  tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);
+
+  A carry_in[K];
+  bool open[K];
+  A warp_agg;
+  bool warp_has_head;
+  tile_pass1<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+  if(lane == 0) {
+    s_wagg[warp] = warp_agg;
+    s_wflag[warp] = warp_has_head ? 1 : 0;
+  }
+  __syncthreads();
+  A my_prefix, tile_agg;
+  bool my_open, tile_has_head;
+  combine_warps<A, MODE, C::NW>(s_wagg, s_wflag, warp, my_prefix, my_open, tile_agg, tile_has_head);
+
   A tile_prefix = A(0);
   if(use_lookback) {
     if(warp == 0) {
@@ -252,49 +537,228 @@ scan_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t
     tile_prefix = s_prefix;
   }
   const A warp_prefix = my_prefix + (my_open ? tile_prefix : A(0));
+  tile_pass2_store<A, MODE, ALIGNED, K>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, exclusive);
+}
 
-  // ---- pass 2: rescan with the known carry, store ---------------------------------------------------
+// ---- kernel 2: persistent, warp-specialised, TMA ring (see header) ---------------------------------------------
+template <typename A, int MODE>
+__global__ void __launch_bounds__(WS_THREADS, SB_WS_MINB)
+scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
+    const A* __restrict__ seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, long long num_tiles) {
+  using C = TileCfg<A, WS_NW, WS_K>;
+  constexpr int VEC = C::VEC;
+  constexpr int K = WS_K;
+  constexpr int NW = WS_NW;
+  extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x TILE_BYTES
+  __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES], agg_bar[WS_NSLOT], prefix_bar[WS_NSLOT];
+  __shared__ A s_wagg[WS_NSLOT][NW];
+  __shared__ int s_wflag[WS_NSLOT][NW];
+  __shared__ A s_tprefix[WS_NSLOT];
+  __shared__ int s_first_head[WS_NSLOT];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long G = gridDim.x;
+  const long long my_tiles = (num_tiles - (long long)blockIdx.x + G - 1) / G;  // tiles blockIdx.x + i*G
+
+  if(threadIdx.x == 0) {
 #pragma unroll
-  for(int j = 0; j < K; ++j) {
-    const size_t idx = wbase + (size_t)j * C::ROW;
-    A r = carry_in[j] + (open[j] ? warp_prefix : A(0));
-    sb::Vec<A> o;
-#pragma unroll
-    for(int c = 0; c < VEC; ++c) {
-      if(MODE != MODE_PLAIN && ((hf[j] >> c) & 1u)) r = A(0);
-      const A e = r;
-      r += v[j][c];
-      o.v[c] = exclusive ? e : r;
+    for(int s = 0; s < WS_STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), NW);
     }
-    if(ALIGNED && (full_tile || idx + VEC <= n)) {
-      sb::stg_vec<A>(out + idx, o);
-    } else {
 #pragma unroll
-      for(int c = 0; c < VEC; ++c)
-        if(idx + c < n) out[idx + c] = o.v[c];
+    for(int s = 0; s < WS_NSLOT; ++s) {
+      mbar_init(smem_u32(&agg_bar[s]), NW);
+      mbar_init(smem_u32(&prefix_bar[s]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();  // the only block-wide barrier
+
+  if(warp == NW) {
+    // ===== producer: TMA bulk loads into the ring =====
+    for(long long i = 0; i < my_tiles; ++i) {
+      const int stage = (int)(i % WS_STAGES);
+      if(i >= WS_STAGES) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)((i / WS_STAGES) - 1) & 1u);
+      const long long tile = (long long)blockIdx.x + i * G;
+      const size_t base = (size_t)tile * C::TILE;
+      const uint32_t bar = smem_u32(&full_bar[stage]);
+      if(base + C::TILE <= n) {
+        if(lane == 0) {
+          mbar_expect_tx(bar, C::TILE_BYTES);
+          bulk_load(smem_u32(ring) + stage * C::TILE_BYTES, in + base, C::TILE_BYTES, bar);
+        }
+      } else {
+        // ragged last tile: guarded copy, zero fill
+        A* dst = reinterpret_cast<A*>(ring + (size_t)stage * C::TILE_BYTES);
+        for(int e = lane; e < C::TILE; e += 32) dst[e] = (base + e < n) ? in[base + e] : A(0);
+        __syncwarp();
+        if(lane == 0) mbar_arrive(bar);
+      }
+    }
+  } else if(warp == NW + 1) {
+    // ===== look-back warp =====
+    if(!use_lookback) return;
+    const typename Desc<A>::word* rdesc = desc + num_tiles;  // one prefix per round behind the tile descriptors
+    for(long long i = 0; i < my_tiles; ++i) {
+      const int slot = (int)(i % WS_NSLOT);
+      const long long tile = (long long)blockIdx.x + i * G;
+      mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(i / WS_NSLOT) & 1u);
+      A my_prefix, tile_agg;
+      bool my_open, tile_has_head;
+      combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], -1, my_prefix, my_open, tile_agg, tile_has_head);
+      if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | (tile_has_head ? ST_INCL : ST_AGG), tile_agg);
+      A p = A(0);
+      const bool starts_on_head = MODE != MODE_PLAIN && s_first_head[slot];
+      if(!starts_on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed);
+      if(lane == 0) {
+        if((tile + 1) % G == 0)
+          Desc<A>::store(const_cast<typename Desc<A>::word*>(rdesc) + tile / G, (epoch << 2) | ST_INCL, tile_has_head ? tile_agg : p + tile_agg);
+        s_tprefix[slot] = p;
+        mbar_arrive(smem_u32(&prefix_bar[slot]));
+      }
+    }
+  } else {
+    if(!use_lookback) {
+      // ===== workers, single phase: every tile starts on a head, so a tile needs nothing from other tiles.
+      // The agg mbarrier doubles as the workers' barrier for the warp pairs of the tile.
+      for(long long it = 0; it < my_tiles; ++it) {
+        const int stage = (int)(it % WS_STAGES), slot = (int)(it % WS_NSLOT);
+        const long long tile = (long long)blockIdx.x + it * G;
+        const size_t base = (size_t)tile * C::TILE;
+        const size_t wbase = base + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
+        const bool full_tile = base + C::TILE <= n;
+        A v[K][VEC];
+        unsigned hf[K];
+        tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);
+        mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / WS_STAGES) & 1u);
+        tile_load_smem<A, K>(v, ring + (size_t)stage * C::TILE_BYTES + (size_t)warp * K * 512);
+        A carry_in[K];
+        bool open[K];
+        A warp_agg;
+        bool warp_has_head;
+        tile_pass1<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+        if(lane == 0) {
+          mbar_arrive(smem_u32(&empty_bar[stage]));  // the tile lives in registers now
+          s_wagg[slot][warp] = warp_agg;
+          s_wflag[slot][warp] = warp_has_head ? 1 : 0;
+          mbar_arrive(smem_u32(&agg_bar[slot]));
+        }
+        A my_prefix = A(0), tile_agg;
+        bool my_open = true, tile_has_head;
+        if(!(MODE != MODE_PLAIN && (sb::shfl_idx(hf[0], 0) & 1u))) {  // a warp chunk that starts on a head needs no one
+          mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(it / WS_NSLOT) & 1u);
+          combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], warp, my_prefix, my_open, tile_agg, tile_has_head);
+        }
+        tile_pass2_store<A, MODE, true, K>(v, hf, carry_in, open, my_prefix, wbase, full_tile, n, out, exclusive);
+      }
+      return;
+    }
+    // ===== workers: phase A runs WS_DEPTH tiles ahead of phase B =====
+    for(long long it = 0; it < my_tiles + WS_DEPTH; ++it) {
+      if(it < my_tiles) {
+        // ---- phase A: tile -> per-warp (sum, has-head) for the look-back warp
+        const int stage = (int)(it % WS_STAGES), slot = (int)(it % WS_NSLOT);
+        const long long tile = (long long)blockIdx.x + it * G;
+        const size_t wbase = (size_t)tile * C::TILE + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
+        A v[K][VEC];
+        unsigned hf[K];
+        tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);
+        mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / WS_STAGES) & 1u);
+        tile_load_smem<A, K>(v, ring + (size_t)stage * C::TILE_BYTES + (size_t)warp * K * 512);
+        A agg;
+        bool has_head;
+        warp_reduce_rows<A, MODE, K>(v, hf, agg, has_head);
+        if(lane == 0) {
+          s_wagg[slot][warp] = agg;
+          s_wflag[slot][warp] = has_head ? 1 : 0;
+          if(warp == 0) s_first_head[slot] = (int)(hf[0] & 1u);
+          mbar_arrive(smem_u32(&agg_bar[slot]));
+        }
+      }
+      if(it >= WS_DEPTH) {
+        // ---- phase B: scan the tile with its prefix, store, release the stage
+        const long long b = it - WS_DEPTH;
+        const int stage = (int)(b % WS_STAGES), slot = (int)(b % WS_NSLOT);
+        const long long tile = (long long)blockIdx.x + b * G;
+        const size_t base = (size_t)tile * C::TILE;
+        const size_t wbase = base + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
+        const bool full_tile = base + C::TILE <= n;
+        A v[K][VEC];
+        unsigned hf[K];
+        tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);
+        tile_load_smem<A, K>(v, ring + (size_t)stage * C::TILE_BYTES + (size_t)warp * K * 512);
+        A carry_in[K];
+        bool open[K];
+        A warp_agg;
+        bool warp_has_head;
+        tile_pass1<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+        // all warps' phase-A pairs of this tile (and, with look-back, the tile prefix) are complete
+        const uint32_t par = (uint32_t)(b / WS_NSLOT) & 1u;
+        A tile_prefix = A(0);
+        if(use_lookback) {
+          mbar_wait(smem_u32(&prefix_bar[slot]), par);
+          tile_prefix = s_tprefix[slot];
+        } else {
+          mbar_wait(smem_u32(&agg_bar[slot]), par);
+        }
+        A my_prefix, tile_agg;
+        bool my_open, tile_has_head;
+        combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], warp, my_prefix, my_open, tile_agg, tile_has_head);
+        const A warp_prefix = my_prefix + (my_open ? tile_prefix : A(0));
+        __syncwarp();
+        if(lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));  // ring reads are done (values live in registers)
+        tile_pass2_store<A, MODE, true, K>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, exclusive);
+      }
     }
   }
+}
+
+// co-resident CTAs per SM of a persistent kernel instantiation (queried once per process)
+template <typename Kern>
+int resident_ctas_per_sm(Kern kern, int threads, size_t smem) {
+  int nb = 0;
+  if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) return 0;
+  return nb;
+}
+
+template <typename A, int MODE>
+int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* flags,
+    const A* seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, size_t tiles) {
+  using C = TileCfg<A, WS_NW, WS_K>;
+  constexpr size_t smem = (size_t)WS_STAGES * C::TILE_BYTES;
+  static const int per_sm = resident_ctas_per_sm(scan_ws_kernel<A, MODE>, WS_THREADS, smem);
+  if(per_sm <= 0) return SB_ERR_WORKSPACE;
+  size_t grid = (size_t)ctx->sm_count * per_sm;
+  if(grid > tiles) grid = tiles;
+  scan_ws_kernel<A, MODE><<<(unsigned)grid, WS_THREADS, smem, ctx->stream>>>(in, out, n, exclusive, seg_len, seg_mask, flags, seed, desc,
+      epoch, use_lookback, (long long)tiles);
+  return SB_OK;
 }
 
 template <typename T>
 int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int mode, size_t seg_len, const uint8_t* flags, const T* seed) {
   using A = typename sb_arith<T>::type;
-  using C = ScanCfg<A>;
   using W = typename Desc<A>::word;
   if(!ctx || (n && (!in || !out))) return SB_ERR_BAD_ARG;
   if(!sb::aligned_to(in, sizeof(T)) || !sb::aligned_to(out, sizeof(T)) || !sb::aligned_to(seed, sizeof(T))) return SB_ERR_MISALIGNED;
   if(n == 0) return SB_OK;
   sb_device_guard guard(ctx->device);
 
-  const size_t tiles = (n + C::TILE - 1) / C::TILE;
+  // persistent kernel for 16-byte aligned buffers with at least a few tiles; ticketed kernel otherwise
+  const bool aligned = sb::aligned_to(in, 16) && sb::aligned_to(out, 16);
+  const size_t ws_tile = TileCfg<A, WS_NW, WS_K>::TILE, simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
+  const bool use_ws = aligned && n >= 4 * ws_tile;
+  const size_t tile = use_ws ? ws_tile : simple_tile;
+  const size_t tiles = (n + tile - 1) / tile;
   if(tiles > 0x7fffffffull) return SB_ERR_BAD_ARG;
+
   size_t seg_mask = ~(size_t)0;
   int use_lookback = 1;
-  if(mode == MODE_IMPLICIT) {
-    if(sb::is_pow2(seg_len)) {
-      seg_mask = seg_len - 1;
-      if(seg_len <= (size_t)C::TILE) use_lookback = 0;  // every tile starts on a head
-    }
+  if(mode == MODE_IMPLICIT && sb::is_pow2(seg_len)) {
+    seg_mask = seg_len - 1;
+    if(seg_len <= tile) use_lookback = 0;  // every tile starts on a head
   }
   if(tiles == 1 && !(mode == MODE_PLAIN && seed)) use_lookback = 0;
 
@@ -302,7 +766,8 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   uint32_t epoch = 0;
   unsigned long long tbase = 0;
   if(use_lookback) {
-    int rc = sb_ctx_reserve_desc(ctx, sizeof(A) == 4 ? tiles : 0, sizeof(A) == 8 ? tiles : 0);
+    const size_t ndesc = 2 * tiles + 64;  // tile descriptors + (persistent kernel) one prefix per round
+    int rc = sb_ctx_reserve_desc(ctx, sizeof(A) == 4 ? ndesc : 0, sizeof(A) == 8 ? ndesc : 0);
     if(rc != SB_OK) return rc;
     if(ctx->scan_epoch >= (1u << 30) - 1) {
       if(ctx->desc64) SB_CUDA_TRY(cudaMemsetAsync(ctx->desc64, 0, ctx->desc64_count * 8, ctx->stream));
@@ -311,13 +776,23 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
     }
     epoch = ++ctx->scan_epoch;
     desc = reinterpret_cast<W*>(sizeof(A) == 4 ? ctx->desc64 : ctx->desc128);
-    tbase = ctx->scan_ticket_base;
-    ctx->scan_ticket_base += tiles;
+    if(!use_ws) {
+      tbase = ctx->scan_ticket_base;
+      ctx->scan_ticket_base += tiles;
+    }
   }
-  const bool aligned = sb::aligned_to(in, 16) && sb::aligned_to(out, 16);
   const A* ain = reinterpret_cast<const A*>(in);
   A* aout = reinterpret_cast<A*>(out);
   const A* aseed = reinterpret_cast<const A*>(seed);
+  if(use_ws) {
+    int rc;
+    if(mode == MODE_PLAIN) rc = launch_ws<A, MODE_PLAIN>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else if(mode == MODE_IMPLICIT) rc = launch_ws<A, MODE_IMPLICIT>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else rc = launch_ws<A, MODE_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    if(rc != SB_OK) return rc;
+    SB_CHECK_LAUNCH(ctx);
+    return SB_OK;
+  }
   const dim3 grid((unsigned)tiles), block(SCAN_NT);
 #define SB_SCAN_LAUNCH(MODE_, AL_)                                                                                       \
   scan_kernel<A, MODE_, AL_><<<grid, block, 0, ctx->stream>>>(ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, \
@@ -350,6 +825,8 @@ int segscan_impl(sb_ctx* ctx, const T* in, T* out, size_t n, size_t seg_len, con
 }
 
 }  // namespace
+
+size_t sb_scan_tile_bytes() { return (size_t)WS_NW * WS_K * 512; }
 
 extern "C" {
 int sb_scan_i32(sb_ctx* c, const int32_t* in, int32_t* out, size_t n, int ex, size_t g, const int32_t* seed) { return scan_impl<int32_t>(c, in, out, n, ex, g, seed); }

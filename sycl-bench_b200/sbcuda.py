@@ -21,6 +21,11 @@ class SbError(RuntimeError):
 
 
 def lib_path() -> str:
+    # SB_CUDA_LIB selects a tuning variant built by `make tune` (profiles/tune_scan.py); it must still be
+    # an in-tree libsb_cuda build — there is no other backend.
+    override = os.environ.get("SB_CUDA_LIB")
+    if override:
+        return os.path.abspath(override)
     return os.path.join(_HERE, "lib", "libsb_cuda.so")
 
 
