@@ -141,6 +141,10 @@ def run_ours(args):
         ctx.iota(x[t], offset=rank * n)  # global iota: shard r starts at r * n
     torch.cuda.synchronize()
 
+    from sycl_bench_b200 import sharded
+
+    ops = sharded.for_context(ctx, dist, rank, world)
+
     def step(events=None):
         """one pass of the hot path; `events` collects (leg, start, end) CUDA events"""
         for op, t in LEGS:
@@ -148,17 +152,9 @@ def run_ours(args):
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
             if op == "reduce":
-                ctx.reduce(x[t], red[t])
-                if world > 1:
-                    dist.all_reduce(red[t])  # ncclSum of one element per rank
+                ops.reduce(x[t], red[t])  # N>1: + ncclSum all-reduce of one element per rank
             else:
-                if world == 1:
-                    ctx.scan(x[t], y[t])
-                else:
-                    ctx.reduce(x[t], carry[t])
-                    dist.all_gather_into_tensor(totals[t], carry[t])
-                    ctx.exclusive_carry(totals[t], rank, carry[t])
-                    ctx.scan(x[t], y[t], seed=carry[t])
+                ops.prefixsum(x[t], y[t], totals[t], carry[t], strategy=args.scan_strategy)
             if events is not None:
                 e1.record()
                 events.append(((op, t), e0, e1))
@@ -238,7 +234,7 @@ def run_ours(args):
             "config": {"workload": f"pattern/reduction + pattern/prefixsum, fp32 and int64, --size=2^{args.log2n} per GPU (BASELINE configs[1])",
                        "elements_per_gpu": n, "legs": [f"{op}_{t}" for op, t in LEGS],
                        "l2": "inputs 1-4 GiB per leg, larger than the 126 MB L2; no flush needed",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} shards; reduce: all-reduce(1 elt); prefixsum: reduce -> all-gather totals -> seeded scan"},
+                       "parallelism": "1 GPU" if world == 1 else f"{world} contiguous shards; reduce: NCCL all-reduce(1 elt); prefixsum: {args.scan_strategy} with NCCL all-gather of shard totals"},
             "elements_per_s": round(4 * n * world / (ms_per_step * 1e-3), 1),
             "verified": bool(ok),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -366,6 +362,8 @@ def main():
     ap.add_argument("--cpu-log2n", type=int, default=26, help="CPU-baseline sample size")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scan-strategy", default="reduce_then_scan", choices=["reduce_then_scan", "scan_then_carry"],
+                    help="N>1 prefix sum: 3-pass reduce -> exchange -> seeded scan (default) or the 4-pass scan -> exchange -> carry-add")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

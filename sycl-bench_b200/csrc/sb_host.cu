@@ -124,7 +124,7 @@ size_t sb_workspace_bytes(int op, int dtype, size_t n) {
   case SB_OP_SEGSCAN: {
     const size_t tile = sb_scan_tile_bytes() / s;
     const size_t tiles = (n + tile - 1) / tile;
-    return tiles * (s == 4 ? 8 : 16) + 256;
+    return (2 * tiles + 64) * (s == 4 ? 8 : 16) + 256;  // tile descriptors + per-round prefixes + ticket
   }
   case SB_OP_SEGREDUCE: return 0;
   default: return 0;

@@ -1,0 +1,4 @@
+// Same include name as /root/reference/include/common.h so that benchmark sources keep their
+// #include lines; the SYCL-free implementation lives in sb_harness.h.
+#pragma once
+#include "sb_harness.h"

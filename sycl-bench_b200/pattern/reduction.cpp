@@ -1,0 +1,94 @@
+// pattern/reduction — global sum of in[i] = (T)i, drop-in for /root/reference/pattern/reduction.cpp.
+//
+// Same plugin surface (ctor(args) / setup() / run(events) / verify() / getBenchmarkName), same row
+// names (Pattern_Reduction_NDRange_{int32,int64,fp32,fp64}, reduction.cpp:177-182,210-216), same
+// flags.  The multi-pass work-group tree of the reference (submit(), :71-97) is ONE sb_reduce_<T>
+// launch.  Differences, all documented in DESIGN.md:
+//  * only the NDRange rows exist: one CUDA kernel backs the benchmark and is not listed twice
+//    under a second name (upstream's Hierarchical variant computes the same thing, :128-167);
+//  * N % L != 0: the reference silently drops the tail (assert compiled out, :29,:77); so does
+//    this benchmark — it reduces floor(N/L)*L elements;
+//  * verify() checks the value against the closed form (integers bit-exact, floating point within
+//    1e-5*log2 N / 1e-12*log2 N relative).  Upstream's own check (:59-68) accumulates in `int`
+//    and prints FAIL for every N > 65 536; `--reference-verify` reproduces that verdict verbatim.
+#include "pattern_common.h"
+
+template <typename T>
+class Reduction {
+protected:
+  BenchmarkArgs _args;
+  PrefetchedBuffer<T> _input_buff;
+  PrefetchedBuffer<T> _output_buff;
+  std::size_t _n = 0;  // elements actually reduced
+
+public:
+  Reduction(const BenchmarkArgs& args) : _args{args} {}
+
+  void setup() {
+    const std::size_t L = std::max<std::size_t>(_args.local_size, 1);
+    _n = (_args.problem_size / L) * L;
+    if(_args.cli.isFlagSet("--host-input")) {
+      // generate_input() on the host and upload, like upstream setup() (:31-42)
+      std::vector<T> host(_args.problem_size);
+      for(std::size_t i = 0; i < host.size(); ++i) host[i] = static_cast<T>(i);
+      _input_buff.initialize(_args.ctx(), host.data(), host.size());
+    } else {
+      _input_buff.initialize(_args.ctx(), _args.problem_size);
+      sb::check(pattern::Ops<T>::iota(_args.ctx(), _input_buff.get(), _args.problem_size, 0), "sb_iota");
+    }
+    _output_buff.initialize(_args.ctx(), 1);  // upstream allocates N elements of scratch (:41); one is enough
+  }
+
+  void run(std::vector<sb::event>& events) {
+    sb::check(pattern::Ops<T>::reduce(_args.ctx(), _input_buff.get(), _n, _output_buff.get()), "sb_reduce");
+    events.push_back({"sb_reduce"});
+  }
+
+  bool verify(VerificationSetting&) {
+    const T result = _output_buff.get_host_access()[0];
+    if(_args.cli.isFlagSet("--reference-verify")) return reference_verify(result);
+    const uint64_t exact = _n == 0 ? 0 : pattern::tri(_n - 1);
+    const long double real = _n == 0 ? 0.0L : pattern::tri_ld((long double)(_n - 1));
+    return pattern::value_matches<T>(result, exact, real, _n);
+  }
+
+  static ThroughputMetric getThroughputMetric(const BenchmarkArgs& args) {
+    const std::size_t L = std::max<std::size_t>(args.local_size, 1);
+    const double n = static_cast<double>((args.problem_size / L) * L);
+    return {(n * sizeof(T) + sizeof(T)) / 1073741824.0, "GiB"};  // algorithmic bytes: N*s + s
+  }
+
+private:
+  // upstream verify(), reduction.cpp:59-68, restated: the fp64 inputs are summed by std::reduce with
+  // the init value `0`, an int, so the accumulator is an int (x86 cvttsd2si: out of range -> INT_MIN)
+  bool reference_verify(T result) const {
+    int acc = 0;
+    for(std::size_t i = 0; i < _args.problem_size; ++i) {
+      const double s = static_cast<double>(acc) + static_cast<double>(i);
+      acc = (s >= 2147483648.0 || s < -2147483648.0 || s != s) ? INT_MIN : static_cast<int>(s);
+    }
+    const double delta = static_cast<double>(result) - acc;
+    return std::abs(delta) < 1.e-5;
+  }
+};
+
+template <class T>
+class ReductionNDRange : public Reduction<T> {
+public:
+  ReductionNDRange(const BenchmarkArgs& args) : Reduction<T>{args} {}
+  static std::string getBenchmarkName(BenchmarkArgs&) { return std::string("Pattern_Reduction_NDRange_") + ReadableTypename<T>::name; }
+};
+
+int main(int argc, char** argv) {
+  BenchmarkApp app(argc, argv);
+  // short is excluded upstream as well: it overflows for tiny sizes (reduction.cpp:207-209)
+  if(app.shouldRunNDRangeKernels()) {
+    app.run<ReductionNDRange<int>>();
+    app.run<ReductionNDRange<long long>>();
+    app.run<ReductionNDRange<float>>();
+    app.run<ReductionNDRange<double>>();
+  } else {
+    std::cerr << "reduction: --no-ndrange-kernels leaves nothing to run (one CUDA kernel backs the NDRange rows; see DESIGN.md)\n";
+  }
+  return app.exitCode();
+}

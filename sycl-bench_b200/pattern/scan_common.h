@@ -1,0 +1,66 @@
+// prefixsum / scan / segmentedscan share one benchmark class: upstream's three files are TODO
+// stubs (/root/reference/pattern/prefixsum.cpp:1, scan.cpp:1, segmentedscan.cpp:1), so the
+// semantics are the written contract of DESIGN.md §Scan semantics.
+#pragma once
+#include "pattern_common.h"
+
+namespace pattern {
+
+enum class ScanKind { PrefixSum, ScanGlobal, ScanGroup, SegScanImplicit, SegScanFlags };
+
+template <typename T, ScanKind KIND>
+class ScanBenchmark {
+protected:
+  BenchmarkArgs _args;
+  PrefetchedBuffer<T> _in, _out;
+  PrefetchedBuffer<uint8_t> _flags;
+
+  static constexpr bool exclusive() { return KIND == ScanKind::ScanGlobal || KIND == ScanKind::ScanGroup; }
+  std::size_t restart() const { return (KIND == ScanKind::PrefixSum || KIND == ScanKind::ScanGlobal) ? 0 : _args.local_size; }
+
+public:
+  ScanBenchmark(const BenchmarkArgs& args) : _args{args} {}
+
+  void setup() {
+    const std::size_t n = _args.problem_size;
+    if(KIND != ScanKind::PrefixSum && KIND != ScanKind::ScanGlobal && _args.local_size == 0)
+      throw std::invalid_argument("--local must be positive");
+    _in.initialize(_args.ctx(), n);
+    _out.initialize(_args.ctx(), n);
+    sb::check(Ops<T>::iota(_args.ctx(), _in.get(), n, 0), "sb_iota");
+    if(KIND == ScanKind::SegScanFlags) {
+      std::vector<uint8_t> f(n, 0);
+      for(std::size_t i = 0; i < n; i += _args.local_size) f[i] = 1;
+      _flags.initialize(_args.ctx(), f.data(), n);
+    }
+  }
+
+  void run(std::vector<sb::event>& events) {
+    const std::size_t n = _args.problem_size;
+    int rc;
+    if(KIND == ScanKind::PrefixSum) rc = Ops<T>::scan(_args.ctx(), _in.get(), _out.get(), n, 0, 0);
+    else if(KIND == ScanKind::ScanGlobal) rc = Ops<T>::scan(_args.ctx(), _in.get(), _out.get(), n, 1, 0);
+    else if(KIND == ScanKind::ScanGroup) rc = Ops<T>::scan(_args.ctx(), _in.get(), _out.get(), n, 1, _args.local_size);
+    else if(KIND == ScanKind::SegScanImplicit) rc = Ops<T>::segscan(_args.ctx(), _in.get(), _out.get(), n, _args.local_size, nullptr, 0);
+    else rc = Ops<T>::segscan(_args.ctx(), _in.get(), _out.get(), n, 0, _flags.get(), 0);
+    sb::check(rc, "sb_scan");
+    events.push_back({"sb_scan"});
+  }
+
+  bool verify(VerificationSetting&) { return verify_scan<T>(_args.ctx(), _out, _args.problem_size, exclusive(), restart()); }
+
+  static ThroughputMetric getThroughputMetric(const BenchmarkArgs& args) {
+    const double n = static_cast<double>(args.problem_size);
+    return {(2.0 * n * sizeof(T) + (KIND == ScanKind::SegScanFlags ? n : 0.0)) / 1073741824.0, "GiB"};  // 2*N*s (+ N flag bytes)
+  }
+};
+
+#define SB_SCAN_BENCH(CLASS, KIND_, PREFIX)                                                                             \
+  template <class T>                                                                                                    \
+  class CLASS : public pattern::ScanBenchmark<T, pattern::ScanKind::KIND_> {                                            \
+  public:                                                                                                               \
+    CLASS(const BenchmarkArgs& args) : pattern::ScanBenchmark<T, pattern::ScanKind::KIND_>{args} {}                     \
+    static std::string getBenchmarkName(BenchmarkArgs&) { return std::string(PREFIX) + ReadableTypename<T>::name; }     \
+  };
+
+} // namespace pattern

@@ -1,0 +1,107 @@
+"""N > 1 host logic on CPU: world_size 2 and 3 over gloo.  The local operations are the oracle's
+(there is no GPU here); what is under test is the sharding, the exchange and the carry arithmetic of
+sycl-bench_b200/sharded.py, which bench.py runs over NCCL with libsb_cuda as the local backend."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, dtype_name, strategy, q):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    from oracle import oracle as O
+
+    pkg = ge.load_package()
+    from sycl_bench_b200 import sharded
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t = {"i32": torch.int32, "i64": torch.int64, "f64": torch.float64}[dtype_name]
+
+    def o_reduce(x, out):
+        out[0] = int(O.cpu_sum(dtype_name, x.numpy())) if dtype_name[0] == "i" else float(O.cpu_sum(dtype_name, x.numpy()))
+
+    def o_scan(x, y, exclusive, seed):
+        r = O.scan(dtype_name, x.numpy(), exclusive)
+        y.copy_(torch.from_numpy(r))
+        if seed is not None:
+            y.add_(seed)
+
+    def o_carry_add(y, c):
+        y.add_(c)
+
+    def o_excl(totals, r, c):
+        c[0] = totals[:r].sum() if r else 0
+
+    ops = sharded.ShardedOps(dist, rank, world, o_reduce, o_scan, o_carry_add, o_excl)
+    b, e = sharded.shard_bounds(n, world, rank)
+    x = torch.from_numpy(O.iota(dtype_name, e - b, b))
+    out = torch.zeros(1, dtype=t)
+    ops.reduce(x, out)
+    y = torch.empty_like(x)
+    totals, carry = torch.zeros(world, dtype=t), torch.zeros(1, dtype=t)
+    ops.prefixsum(x, y, totals, carry, strategy=strategy)
+    q.put((rank, b, e, out.item(), y.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,dtype_name,strategy", [
+    (2, "i32", "reduce_then_scan"), (2, "i32", "scan_then_carry"), (2, "i64", "reduce_then_scan"),
+    (2, "f64", "scan_then_carry"), (3, "i64", "scan_then_carry"), (3, "i32", "reduce_then_scan"),
+])
+def test_sharded_reduce_and_prefixsum(world, dtype_name, strategy):
+    from oracle import oracle as O
+
+    n = 100003 if dtype_name != "i32" else (1 << 17) + 5  # int32 wraps: the carry arithmetic must wrap too
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, dtype_name, strategy, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = O.iota(dtype_name, n)
+    want_scan = O.scan(dtype_name, full)
+    want_sum = O.wrap(O.kat_reduce(n), dtype_name) if dtype_name[0] == "i" else float(n) * (n - 1) / 2
+    got = np.concatenate([r[4] for r in results])
+    assert [r[1] for r in results][0] == 0 and results[-1][2] == n
+    for r in results:
+        assert r[3] == want_sum
+    assert np.array_equal(got, want_scan)
+
+
+def test_shard_bounds():
+    import __graft_entry__ as ge
+
+    ge.load_package()
+    from sycl_bench_b200.sharded import shard_bounds
+
+    for n, world, align in [(1 << 33, 8, 1), (1000, 3, 1), (1 << 29, 8, 1024), (10, 4, 4), (5, 8, 1)]:
+        spans = [shard_bounds(n, world, r, align) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for (b0, e0), (b1, e1) in zip(spans, spans[1:]):
+            assert e0 == b1 and b0 <= e0
+        for (b, e), (b1, e1) in zip(spans, spans[1:]):
+            if e1 > b1:  # a shard followed by a non-empty shard ends on a segment boundary
+                assert (e - b) % align == 0
+    assert shard_bounds(1 << 33, 8, 3) == (3 << 30, 4 << 30)
