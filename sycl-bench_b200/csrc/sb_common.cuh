@@ -124,6 +124,11 @@ __device__ __forceinline__ uint16_t warp_sum<uint16_t>(uint16_t v) {
   return (uint16_t)__reduce_add_sync(SB_FULL_MASK, (uint32_t)v);
 }
 
+// types whose warp sum is a single redux.sync
+template <typename T> struct has_redux { static constexpr bool value = false; };
+template <> struct has_redux<uint32_t> { static constexpr bool value = true; };
+template <> struct has_redux<uint16_t> { static constexpr bool value = true; };
+
 template <typename T>
 __device__ __forceinline__ T shfl_up(T v, int d) { return __shfl_up_sync(SB_FULL_MASK, v, d); }
 template <typename T>

@@ -370,16 +370,64 @@ __device__ __forceinline__ void warp_reduce_rows(const A (&v)[K][16 / sizeof(A)]
   has_head = runf;
 }
 
-// pass 1: thread partials -> per-row warp segmented scan.  carry_in[j] = running sum entering the
-// thread's part of row j, relative to the start of the warp chunk (or the last head inside it);
-// open[j] = no head between the start of the warp chunk and that point.
+// pass 1: thread partials -> per-row warp segmented scan.  The K row scans are independent shuffle
+// chains (the compiler interleaves them: ILP K); the carries between rows are added afterwards.
+// carry_in[j] = running sum entering the thread's part of row j, relative to the start of the warp
+// chunk (or the last head inside it); open[j] = no head between the start of the chunk and there.
+// Segmented variant of pass 1 with the row scans chained through the carry: fewer live registers
+// (no per-row totals / head masks), which matters more than ILP once head flags are in play.
 template <typename A, int MODE, int K>
-__device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A (&carry_in)[K], bool (&open)[K],
-    A& warp_agg, bool& warp_has_head) {
+__device__ __forceinline__ void tile_pass1_chained(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A (&carry_in)[K],
+    bool (&open)[K], A& warp_agg, bool& warp_has_head) {
   constexpr int VEC = 16 / sizeof(A);
   const int lane = threadIdx.x & 31;
   A row_carry = A(0);
   bool warp_open = true;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    A s = A(0);
+    bool f = false;
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) {
+      if((hf[j] >> c) & 1u) {
+        s = v[j][c];
+        f = true;
+      } else {
+        s += v[j][c];
+      }
+    }
+    const unsigned hm = __ballot_sync(SB_FULL_MASK, f);
+    const unsigned m = hm & (0xffffffffu >> (31 - lane));
+    const int h = m ? 31 - __clz(m) : 0;
+    if(lane == 0 && !f) s += row_carry;
+    A inc = s;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1) {
+      const A t = sb::shfl_up(inc, d);
+      if(lane >= h + d) inc += t;
+    }
+    A ex = sb::shfl_up(inc, 1);
+    if(lane == 0) ex = row_carry;
+    carry_in[j] = ex;
+    open[j] = warp_open && (hm & ((1u << lane) - 1u)) == 0u;
+    row_carry = sb::shfl_idx(inc, 31);
+    if(hm) warp_open = false;
+  }
+  warp_agg = row_carry;
+  warp_has_head = !warp_open;
+}
+
+template <typename A, int MODE, int K>
+__device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A (&carry_in)[K], bool (&open)[K],
+    A& warp_agg, bool& warp_has_head) {
+  if(MODE != MODE_PLAIN) {
+    tile_pass1_chained<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+    return;
+  }
+  constexpr int VEC = 16 / sizeof(A);
+  const int lane = threadIdx.x & 31;
+  A tot[K];          // row sum since the last head of the row (whole row if it has none)
+  unsigned hm[K];    // lanes of row j that contain a head
 #pragma unroll
   for(int j = 0; j < K; ++j) {
     A s = A(0);
@@ -393,28 +441,38 @@ __device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], cons
         s += v[j][c];
       }
     }
-    unsigned hm = 0;
+    hm[j] = 0;
     int h = 0;
     if(MODE != MODE_PLAIN) {
-      hm = __ballot_sync(SB_FULL_MASK, f);
-      const unsigned m = hm & (0xffffffffu >> (31 - lane));
+      hm[j] = __ballot_sync(SB_FULL_MASK, f);
+      const unsigned m = hm[j] & (0xffffffffu >> (31 - lane));
       h = m ? 31 - __clz(m) : 0;
     }
-    if(lane == 0 && !f) s += row_carry;
     A inc = s;
 #pragma unroll
     for(int d = 1; d < 32; d <<= 1) {
       const A t = sb::shfl_up(inc, d);
       if(lane >= h + d) inc += t;
     }
-    A ex = sb::shfl_up(inc, 1);
-    if(lane == 0) ex = row_carry;
-    carry_in[j] = ex;
-    open[j] = warp_open && (MODE == MODE_PLAIN || (hm & ((1u << lane) - 1u)) == 0u);
-    row_carry = sb::shfl_idx(inc, 31);
-    if(MODE != MODE_PLAIN && hm) warp_open = false;
+    const A ex = sb::shfl_up(inc, 1);
+    carry_in[j] = lane == 0 ? A(0) : ex;
+    tot[j] = sb::shfl_idx(inc, 31);
   }
-  warp_agg = row_carry;
+  A off = A(0);
+  bool warp_open = true;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    const bool row_open = MODE == MODE_PLAIN || (hm[j] & ((1u << lane) - 1u)) == 0u;  // no head in front of me in this row
+    if(row_open) carry_in[j] += off;
+    open[j] = warp_open && row_open;
+    if(MODE != MODE_PLAIN && hm[j]) {
+      off = tot[j];
+      warp_open = false;
+    } else {
+      off += tot[j];
+    }
+  }
+  warp_agg = off;
   warp_has_head = !warp_open;
 }
 
