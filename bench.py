@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py — headline benchmark of the pattern/ reduce + prefix-sum hot path on B200.
 
-Workload (BASELINE.json configs[1]): pattern/reduction + pattern/prefixsum, fp32 and int64,
+Default workload = BASELINE.json configs[1]: pattern/reduction + pattern/prefixsum, fp32 and int64,
 --size=2^28 per GPU, iota input (pattern/reduction.cpp:31-34 of the reference).  One *step* is one
 pass of the hot path over that batch: 4 libsb_cuda launches
 
@@ -12,15 +12,18 @@ Metric: effective HBM GB/s = algorithmic bytes (reduce N*s + s, 
 `value` is timed with inputs resident in HBM; `e2e` goes through the host-buffer C-ABI calls
 (sb_host_reduce / sb_host_scan) from pinned host memory, H2D + D2H inside the timed region.
 
-N > 1 (torchrun, one rank per GPU, weak scaling): every rank owns a 2^28-element shard of a global
-N*2^28 problem.  reduction = local sb_reduce + NCCL all-reduce of one element; prefix sum = local
-sb_reduce -> NCCL all-gather of the shard totals -> sb_exclusive_carry -> seeded sb_scan (the shard is
-read twice and written once: 3 instead of the 4 passes of scan + carry-add).
+N > 1 (torchrun, one rank per GPU): every rank owns a contiguous shard.  reduction = local sb_reduce
++ NCCL all-reduce of one element; prefix sum = local sb_reduce -> NCCL all-gather of the shard totals
+-> sb_exclusive_carry -> seeded sb_scan (the shard is read twice and written once: 3 instead of the 4
+passes of scan + carry-add; --scan-strategy scan_then_carry runs the 4-pass recipe).
+`--workload config2` (default): weak scaling, 2^28 elements per GPU.
+`--workload config5`: BASELINE configs[4], reduction + prefixsum int32, 2^33 elements in total
+(strong scaling: 2^33 / N per GPU).
 
 `--impl reference` times the reference's own CPU implementation on the host cores instead:
-oracle/_ref/reduction (the unmodified pattern/reduction.cpp on the host SYCL shim) for the two
-reduction legs, and the oracle's OpenMP port for the two prefix-sum legs (upstream prefixsum.cpp
-is a TODO stub), on a bounded 2^26-element sample.
+oracle/_ref/reduction (the unmodified pattern/reduction.cpp on the host SYCL shim) for the
+reduction legs, and the oracle's OpenMP port for the prefix-sum legs (upstream prefixsum.cpp is a
+TODO stub), on a bounded 2^26-element sample.
 """
 from __future__ import annotations
 
@@ -35,11 +38,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LOG2_N = 28
-GIB = float(1 << 30)
-LEGS = (("reduce", "f32"), ("reduce", "i64"), ("scan", "f32"), ("scan", "i64"))
 SIZE = {"f32": 4, "i64": 8, "i32": 4, "f64": 8}
 METRIC = "pattern reduce/scan effective HBM GB/s"
+WORKLOADS = {
+    "config2": {"legs": (("reduce", "f32"), ("reduce", "i64"), ("scan", "f32"), ("scan", "i64")), "log2_per_gpu": 28, "scaling": "weak",
+                "name": "pattern/reduction + pattern/prefixsum, fp32 and int64, --size=2^28 per GPU (BASELINE configs[1])"},
+    "config5": {"legs": (("reduce", "i32"), ("scan", "i32")), "log2_total": 33, "scaling": "strong",
+                "name": "pattern/reduction + pattern/prefixsum, int32, --size=2^33 in total, sharded (BASELINE configs[4])"},
+}
+REF_ROW = {"f32": "Pattern_Reduction_Hierarchical_fp32", "i64": "Pattern_Reduction_Hierarchical_int64",
+           "i32": "Pattern_Reduction_Hierarchical_int32", "f64": "Pattern_Reduction_Hierarchical_fp64"}
 
 
 def algorithmic_bytes(op: str, t: str, n: int) -> int:
@@ -79,8 +87,9 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.3)  # let the sampler come up before the timed region starts
         except Exception:
             self.proc = None
 
@@ -119,6 +128,8 @@ def run_ours(args):
     import __graft_entry__ as ge
 
     pkg = ge.load_package()
+    from sycl_bench_b200 import sharded
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -130,24 +141,30 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     ctx = pkg.Context(local_rank, torch.cuda.current_stream().cuda_stream)
 
-    n = 1 << args.log2n
-    tdt = {"f32": torch.float32, "i64": torch.int64}
-    x = {t: torch.empty(n, dtype=tdt[t], device=dev) for t in ("f32", "i64")}
-    y = {t: torch.empty(n, dtype=tdt[t], device=dev) for t in ("f32", "i64")}
-    red = {t: torch.zeros(1, dtype=tdt[t], device=dev) for t in ("f32", "i64")}
-    totals = {t: torch.zeros(world, dtype=tdt[t], device=dev) for t in ("f32", "i64")}
-    carry = {t: torch.zeros(1, dtype=tdt[t], device=dev) for t in ("f32", "i64")}
-    for t in x:
-        ctx.iota(x[t], offset=rank * n)  # global iota: shard r starts at r * n
+    wl = WORKLOADS[args.workload]
+    legs = wl["legs"]
+    if args.log2n:
+        n = 1 << args.log2n
+    elif "log2_per_gpu" in wl:
+        n = 1 << wl["log2_per_gpu"]
+    else:
+        n = (1 << wl["log2_total"]) // world
+    first = rank * n  # global index of this shard's first element
+    types = sorted({t for _, t in legs})
+    tdt = {"f32": torch.float32, "i64": torch.int64, "i32": torch.int32, "f64": torch.float64}
+    x = {t: torch.empty(n, dtype=tdt[t], device=dev) for t in types}
+    y = {t: torch.empty(n, dtype=tdt[t], device=dev) for t in types}
+    red = {t: torch.zeros(1, dtype=tdt[t], device=dev) for t in types}
+    totals = {t: torch.zeros(world, dtype=tdt[t], device=dev) for t in types}
+    carry = {t: torch.zeros(1, dtype=tdt[t], device=dev) for t in types}
+    for t in types:
+        ctx.iota(x[t], offset=first)
     torch.cuda.synchronize()
-
-    from sycl_bench_b200 import sharded
-
     ops = sharded.for_context(ctx, dist, rank, world)
 
     def step(events=None):
         """one pass of the hot path; `events` collects (leg, start, end) CUDA events"""
-        for op, t in LEGS:
+        for op, t in legs:
             if events is not None:
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -191,51 +208,71 @@ def run_ours(args):
         launches = int(lt.item())
     ms_per_step = ms_total / args.steps
 
-    # correctness of what was timed (integers exact via closed forms; global problem of world * n)
-    mism = torch.zeros(1, dtype=torch.int64, device=dev)
-    ctx.check_iota(y["i64"], mism, offset=rank * n, kind=0)
+    # correctness of what was timed: integer legs exactly, through closed forms of the GLOBAL problem
     ntot = world * n
-    want_sum = (ntot * (ntot - 1) // 2) & ((1 << 64) - 1)
-    got_sum = int(red["i64"].item()) & ((1 << 64) - 1)
-    ok = int(mism.item()) == 0 and got_sum == want_sum
+    ok = True
+    for op, t in legs:
+        if t[0] != "i":
+            continue
+        bits = 8 * SIZE[t]
+        if op == "reduce":
+            want = (ntot * (ntot - 1) // 2) & ((1 << bits) - 1)
+            ok = ok and (int(red[t].item()) & ((1 << bits) - 1)) == want
+        else:
+            mism = torch.zeros(1, dtype=torch.int64, device=dev)
+            ctx.check_iota(y[t], mism, offset=first, kind=0)
+            ok = ok and int(mism.item()) == 0
+    if world > 1:
+        okt = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        ok = bool(okt.item())
 
     per_leg = {}
     for leg, e0, e1 in events:
         per_leg.setdefault(leg, []).append(e0.elapsed_time(e1))
     leg_ms = {f"{op}_{t}": sum(v) / len(v) for (op, t), v in per_leg.items()}
 
-    step_bytes = sum(algorithmic_bytes(op, t, n) for op, t in LEGS) * world
+    step_bytes = sum(algorithmic_bytes(op, t, n) for op, t in legs) * world
     value = step_bytes / (ms_per_step * 1e-3) / 1e9
     peak, peak_src = measured_peak()
-    dom = "scan_i64"
-    dom_bytes = algorithmic_bytes("scan", "i64", n)
+    dom = max((f"{op}_{t}" for op, t in legs), key=lambda k: leg_ms[k])
+    dom_op, dom_t = dom.split("_")
+    dom_bytes = algorithmic_bytes(dom_op, dom_t, n)
     achieved = dom_bytes / (leg_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "scan_kernel<u64, plain> (sb_scan_i64, 2^28 inclusive)", "achieved": round(achieved, 1),
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic_from_profiles(dom), "algorithmic_bytes_per_launch": dom_bytes,
-                "launch_ms": round(leg_ms[dom], 4),
-                "per_leg": {k: {"ms": round(v, 4), "GBps": round(algorithmic_bytes(k.split('_')[0], k.split('_')[1], n) / (v * 1e-3) / 1e9, 1),
-                                "frac": round(algorithmic_bytes(k.split('_')[0], k.split('_')[1], n) / (v * 1e-3) / 1e9 / peak, 4)} for k, v in leg_ms.items()}}
+
+    def leg_info(k, v):
+        o, t = k.split("_")
+        g = algorithmic_bytes(o, t, n) / (v * 1e-3) / 1e9
+        return {"ms": round(v, 4), "GBps": round(g, 1), "frac": round(g / peak, 4)}
+
+    kern = {"scan": "scan_ws_kernel<%s, plain> (sb_scan_%s, persistent warp-specialised TMA ring, round look-back)",
+            "reduce": "reduce_kernel<%s, 512, 4> (sb_reduce_%s)"}[dom_op] % (dom_t, dom_t)
+    roofline = {"bound": "hbm", "kernel": kern + ("" if world == 1 else f" + the N>1 exchange ({args.scan_strategy})"),
+                "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                "traffic": traffic_from_profiles(dom) if (world == 1 and n == 1 << 28) else None,
+                "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": round(leg_ms[dom], 4),
+                "per_leg": {k: leg_info(k, v) for k, v in leg_ms.items()}}
 
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H timed) --------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, pkg, ctx, torch, dist, world, rank, dev, n)
+        e2e = run_e2e(args, legs, ctx, torch, dist, world, rank, dev, min(n, 1 << 28), first)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference(args, sample_log2=args.cpu_log2n, steps=1, warmup=0)["cpu_baseline"]
+        cpu = cpu_reference(legs, sample_log2=args.cpu_log2n, steps=1, warmup=1)["cpu_baseline"]
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32+i64", "data": "synthetic (reference iota: in[i]=(T)i, generated on device)",
-            "config": {"workload": f"pattern/reduction + pattern/prefixsum, fp32 and int64, --size=2^{args.log2n} per GPU (BASELINE configs[1])",
-                       "elements_per_gpu": n, "legs": [f"{op}_{t}" for op, t in LEGS],
-                       "l2": "inputs 1-4 GiB per leg, larger than the 126 MB L2; no flush needed",
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+            "dtype": "+".join(types), "data": "synthetic (reference iota: in[i]=(T)i, generated on device)",
+            "config": {"workload": wl["name"], "elements_per_gpu": n, "elements_total": ntot, "legs": [f"{op}_{t}" for op, t in legs],
+                       "l2": "every leg streams >= 1 GiB, larger than the 126 MB L2; no flush needed",
                        "parallelism": "1 GPU" if world == 1 else f"{world} contiguous shards; reduce: NCCL all-reduce(1 elt); prefixsum: {args.scan_strategy} with NCCL all-gather of shard totals"},
-            "elements_per_s": round(4 * n * world / (ms_per_step * 1e-3), 1),
+            "elements_per_s": round(len(legs) * ntot / (ms_per_step * 1e-3), 1),
+            "frac_of_aggregate_measured_peak": round(value / (peak * world), 4),
             "verified": bool(ok),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
@@ -246,17 +283,18 @@ def run_ours(args):
     return 0 if ok else 1
 
 
-def run_e2e(args, pkg, ctx, torch, dist, world, rank, dev, n):
-    """Same step through sb_host_reduce / sb_host_scan with pinned host buffers."""
-    tdt = {"f32": torch.float32, "i64": torch.int64}
-    h_in = {t: torch.empty(n, dtype=tdt[t]).pin_memory() for t in ("f32", "i64")}
-    h_out = {t: torch.empty(n, dtype=tdt[t]).pin_memory() for t in ("f32", "i64")}
-    h_red = {t: torch.zeros(1, dtype=tdt[t]).pin_memory() for t in ("f32", "i64")}
-    for t in h_in:  # reference input, built on the host like generate_input()
-        h_in[t].copy_(torch.arange(rank * n, rank * n + n, dtype=torch.int64).to(tdt[t]))
+def run_e2e(args, legs, ctx, torch, dist, world, rank, dev, n, first):
+    """Same step through sb_host_reduce / sb_host_scan with pinned host buffers (per rank: its shard)."""
+    tdt = {"f32": torch.float32, "i64": torch.int64, "i32": torch.int32, "f64": torch.float64}
+    types = sorted({t for _, t in legs})
+    h_in = {t: torch.empty(n, dtype=tdt[t]).pin_memory() for t in types}
+    h_out = {t: torch.empty(n, dtype=tdt[t]).pin_memory() for t in types}
+    h_red = {t: torch.zeros(1, dtype=tdt[t]).pin_memory() for t in types}
+    for t in types:  # reference input, built on the host like generate_input()
+        h_in[t].copy_(torch.arange(first, first + n, dtype=torch.int64).to(tdt[t]))
 
     def estep():
-        for op, t in LEGS:
+        for op, t in legs:
             if op == "reduce":
                 ctx.host_reduce(h_in[t], h_red[t])
             else:
@@ -276,20 +314,29 @@ def run_e2e(args, pkg, ctx, torch, dist, world, rank, dev, n):
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-    step_bytes = sum(algorithmic_bytes(op, t, n) for op, t in LEGS) * world
-    h2d = sum(n * SIZE[t] for _, t in LEGS)
-    d2h = sum(SIZE[t] if op == "reduce" else n * SIZE[t] for op, t in LEGS)
-    lo, hi = rank * n, rank * n + n  # shard-local results (host calls are per shard)
-    want = (hi * (hi - 1) // 2 - lo * (lo - 1) // 2) & ((1 << 64) - 1)
-    ok = (int(h_out["i64"][-1].item()) & ((1 << 64) - 1)) == want and (int(h_red["i64"].item()) & ((1 << 64) - 1)) == want
+    step_bytes = sum(algorithmic_bytes(op, t, n) for op, t in legs) * world
+    h2d = sum(n * SIZE[t] for _, t in legs)
+    d2h = sum(SIZE[t] if op == "reduce" else n * SIZE[t] for op, t in legs)
+    ok = True
+    lo, hi = first, first + n  # shard-local results (host calls are per shard)
+    for op, t in legs:
+        if t[0] != "i":
+            continue
+        mask = (1 << (8 * SIZE[t])) - 1
+        want = (hi * (hi - 1) // 2 - lo * (lo - 1) // 2) & mask
+        got = int(h_red[t].item()) if op == "reduce" else int(h_out[t][-1].item())
+        ok = ok and (got & mask) == want
     return {"value": round(step_bytes / (dt / steps) / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": round(dt / steps * 1e3, 2), "steps": steps, "verified": bool(ok),
-            "api": "sb_host_reduce / sb_host_scan (C ABI, pinned host buffers; per-rank shards are independent at N>1)"}
+            "ms_per_step": round(dt / steps * 1e3, 2), "steps": steps, "elements_per_gpu": n, "verified": bool(ok),
+            "api": "sb_host_reduce / sb_host_scan (C ABI, pinned host buffers, 64 MiB chunks, D2H of chunk k-1 overlaps H2D of chunk k; per-rank shards are independent at N>1)"}
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference(args, sample_log2: int, steps: int, warmup: int):
-    """The reference's CPU path on the host cores, bounded sample of the same workload."""
+def cpu_reference(legs, sample_log2: int, steps: int, warmup: int):
+    """The reference's CPU path on the host cores, bounded sample of the same workload.
+    Reduction legs: ONE invocation of oracle/_ref/reduction with --num-runs = warmup + steps; a leg's
+    time is the mean of its `steps` fastest run-time samples (the CSV lists them sorted).
+    Prefix-sum legs: in-process OpenMP scan, `warmup` untimed + `steps` timed calls."""
     import numpy as np
     from oracle import oracle as O
 
@@ -297,36 +344,40 @@ def cpu_reference(args, sample_log2: int, steps: int, warmup: int):
     threads = O.num_threads()
     O.lib()
     have_ref = O.ref_available("reduction")
-    x = {"f32": O.iota("f32", n), "i64": O.iota("i64", n)}
+    types = sorted({t for _, t in legs})
+    x = {t: O.iota(t, n) for t in types}
     out = {t: np.empty_like(v) for t, v in x.items()}
-    name = {"f32": "Pattern_Reduction_Hierarchical_fp32", "i64": "Pattern_Reduction_Hierarchical_int64"}
-
-    def one_step():
-        t_leg = {}
+    leg = {}
+    red_types = [t for op, t in legs if op == "reduce"]
+    if red_types:
         if have_ref:
-            # unmodified pattern/reduction.cpp on the host shim; its own run-time (include/common.h:69-81)
-            rows, _ = O.run_reference("reduction", n, 256, num_runs=1, ndrange=False, verification=False, dump=False)
-            for t in ("f32", "i64"):
-                t_leg[f"reduce_{t}"] = float(rows[name[t]]["run-time-min"])
+            rows, _ = O.run_reference("reduction", n, 256, num_runs=warmup + steps, ndrange=False, verification=False, dump=False, timeout=1800)
+            for t in red_types:
+                samples = sorted(float(v) for v in rows[REF_ROW[t]]["run-time-samples"].strip('"').split())
+                leg[f"reduce_{t}"] = sum(samples[:steps]) / steps
         else:
-            for t in ("f32", "i64"):
-                t0 = time.perf_counter(); O.reduce(t, x[t], 256); t_leg[f"reduce_{t}"] = time.perf_counter() - t0
-        for t in ("f32", "i64"):
-            t0 = time.perf_counter(); O.cpu_scan(t, x[t], out[t]); t_leg[f"scan_{t}"] = time.perf_counter() - t0
-        return t_leg
-
-    for _ in range(warmup):
-        one_step()
-    acc = []
-    for _ in range(steps):
-        acc.append(one_step())
-    leg = {k: sum(a[k] for a in acc) / len(acc) for k in acc[0]}
+            for t in red_types:
+                for _ in range(warmup):
+                    O.reduce(t, x[t], 256)
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    O.reduce(t, x[t], 256)
+                leg[f"reduce_{t}"] = (time.perf_counter() - t0) / steps
+    for op, t in legs:
+        if op != "scan":
+            continue
+        for _ in range(warmup):
+            O.cpu_scan(t, x[t], out[t])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.cpu_scan(t, x[t], out[t])
+        leg[f"scan_{t}"] = (time.perf_counter() - t0) / steps
     sec = sum(leg.values())
-    step_bytes = sum(algorithmic_bytes(op, t, n) for op, t in LEGS)
+    step_bytes = sum(algorithmic_bytes(op, t, n) for op, t in legs)
     value = step_bytes / sec / 1e9
     cpu = {"value": round(value, 3), "unit": "GB/s", "cores": threads, "kind": "reference" if have_ref else "port",
-           "sample": f"same 4 legs at 2^{sample_log2} elements (bounded sample of the 2^{LOG2_N} workload; GB/s is size-independent); "
-                     + ("reduction legs: unmodified reference pattern/reduction.cpp on the host SYCL shim (oracle/_ref, OpenMP), its own run-time; "
+           "sample": f"the same {len(legs)} legs at 2^{sample_log2} elements (bounded sample; GB/s is size-independent); "
+                     + ("reduction legs: unmodified reference pattern/reduction.cpp on the host SYCL shim (oracle/_ref, OpenMP over work-groups), its own run-time; "
                         if have_ref else "reduction legs: oracle restatement of the reference tree (OpenMP); ")
                      + "prefixsum legs: oracle OpenMP two-pass scan (upstream prefixsum.cpp is a TODO stub)",
            "leg_seconds": {k: round(v, 4) for k, v in leg.items()}}
@@ -337,13 +388,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    r = cpu_reference(args, sample_log2=args.cpu_log2n, steps=args.steps, warmup=args.warmup)
+    wl = WORKLOADS[args.workload]
+    r = cpu_reference(wl["legs"], sample_log2=args.cpu_log2n, steps=max(1, args.steps), warmup=max(0, args.warmup))
+    types = sorted({t for _, t in wl["legs"]})
     line = {
         "impl": "reference", "metric": METRIC, "value": round(r["value"], 3), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(r["seconds_per_step"] * 1e3, 2), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32+i64", "data": "synthetic (reference iota)",
-        "config": {"workload": f"pattern/reduction + pattern/prefixsum, fp32 and int64, CPU sample 2^{args.cpu_log2n} of --size=2^{LOG2_N} (BASELINE configs[1])",
-                   "legs": [f"{op}_{t}" for op, t in LEGS]},
+        "warmup": args.warmup, "ms_per_step": round(r["seconds_per_step"] * 1e3, 2), "higher_is_better": True, "scaling": wl["scaling"],
+        "vs_baseline": None, "dtype": "+".join(types), "data": "synthetic (reference iota)",
+        "config": {"workload": wl["name"] + f" — CPU sample of 2^{args.cpu_log2n} elements", "legs": [f"{op}_{t}" for op, t in wl["legs"]]},
         "cpu_baseline": r["cpu_baseline"],
         "e2e": {"value": round(r["value"], 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -358,25 +410,25 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--log2n", type=int, default=LOG2_N, help="elements per GPU = 2^log2n (default: BASELINE configs[1])")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--log2n", type=int, default=0, help="override: elements per GPU = 2^log2n")
     ap.add_argument("--cpu-log2n", type=int, default=26, help="CPU-baseline sample size")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scan-strategy", default="reduce_then_scan", choices=["reduce_then_scan", "scan_then_carry"],
                     help="N>1 prefix sum: 3-pass reduce -> exchange -> seeded scan (default) or the 4-pass scan -> exchange -> carry-add")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.gpus != world:
-        if world == 1 and args.gpus > 1:
-            # convenience: re-exec under torchrun
-            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
-                   "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
-            return subprocess.call(cmd)
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # convenience: re-exec under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
     return run_ours(args)
 
 

@@ -41,6 +41,11 @@ struct sb_ctx {
   void* stage[2] = {nullptr, nullptr};
   size_t stage_bytes[2] = {0, 0};
   void* stage_small = nullptr;  // 64 B result slot
+  // device -> host copies of finished chunks run on a second stream so that they overlap the
+  // host -> device copies of later chunks (PCIe is full duplex)
+  cudaStream_t d2h_stream = nullptr;
+  static constexpr int kChunkEvents = 8;
+  cudaEvent_t chunk_ev[kChunkEvents] = {};
 };
 
 #define SB_CUDA_TRY(expr)                      \

@@ -95,6 +95,12 @@ int sb_ctx_destroy(sb_ctx* ctx) {
   cudaFree(ctx->stage[0]);
   cudaFree(ctx->stage[1]);
   cudaFree(ctx->stage_small);
+  if(ctx->d2h_stream) {
+    cudaStreamSynchronize(ctx->d2h_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
+  }
+  for(cudaEvent_t e : ctx->chunk_ev)
+    if(e) cudaEventDestroy(e);
   if(ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
   if(ctx->ev_end) cudaEventDestroy(ctx->ev_end);
   if(ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -293,6 +293,25 @@ __device__ __forceinline__ void tile_head_flags(unsigned (&hf)[K], size_t wbase,
   }
 }
 
+// explicit head flags staged in the ring by the producer (one flag byte per element, warp chunk at `wflags`):
+// VEC bytes per lane and row, bank-conflict free
+template <typename A, int K>
+__device__ __forceinline__ void tile_head_flags_ring(unsigned (&hf)[K], const unsigned char* wflags, size_t wbase) {
+  constexpr int VEC = 16 / sizeof(A);
+  constexpr int ROW = 32 * VEC;
+  const unsigned char* fp = wflags + (threadIdx.x & 31) * VEC;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    uint32_t w;
+    if(VEC == 4) w = *reinterpret_cast<const uint32_t*>(fp + j * ROW);
+    else w = *reinterpret_cast<const uint16_t*>(fp + j * ROW);
+    hf[j] = 0;
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) hf[j] |= (((w >> (8 * c)) & 0xffu) ? 1u : 0u) << c;
+    if(wbase + (size_t)j * ROW == 0) hf[j] |= 1u;  // element 0 always starts a segment
+  }
+}
+
 // guarded global -> register load of a (possibly partial, possibly unaligned) tile
 template <typename A, bool ALIGNED, int K>
 __device__ __forceinline__ void tile_load_global(A (&v)[K][16 / sizeof(A)], const A* in, size_t wbase, bool full_tile, size_t n) {
@@ -599,15 +618,21 @@ scan_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t
 }
 
 // ---- kernel 2: persistent, warp-specialised, TMA ring (see header) ---------------------------------------------
-template <typename A, int MODE>
+// bytes of one ring stage: the data tile and, for explicit head flags, the tile's flag bytes behind it
+template <typename A, int MODE, int K>
+__host__ __device__ constexpr int ws_stage_bytes() {
+  return TileCfg<A, WS_NW, K>::TILE_BYTES + (MODE == MODE_FLAGS ? TileCfg<A, WS_NW, K>::TILE : 0);
+}
+
+template <typename A, int MODE, int K>
 __global__ void __launch_bounds__(WS_THREADS, SB_WS_MINB)
 scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
-    const A* __restrict__ seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, long long num_tiles) {
-  using C = TileCfg<A, WS_NW, WS_K>;
+    const A* __restrict__ seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, long long num_tiles, int flags_in_ring) {
+  using C = TileCfg<A, WS_NW, K>;
   constexpr int VEC = C::VEC;
-  constexpr int K = WS_K;
   constexpr int NW = WS_NW;
-  extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x TILE_BYTES
+  constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K>();
+  extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x STAGE_BYTES
   __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES], agg_bar[WS_NSLOT], prefix_bar[WS_NSLOT];
   __shared__ A s_wagg[WS_NSLOT][NW];
   __shared__ int s_wflag[WS_NSLOT][NW];
@@ -643,13 +668,19 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
       const uint32_t bar = smem_u32(&full_bar[stage]);
       if(base + C::TILE <= n) {
         if(lane == 0) {
-          mbar_expect_tx(bar, C::TILE_BYTES);
-          bulk_load(smem_u32(ring) + stage * C::TILE_BYTES, in + base, C::TILE_BYTES, bar);
+          const bool with_flags = MODE == MODE_FLAGS && flags_in_ring;
+          mbar_expect_tx(bar, C::TILE_BYTES + (with_flags ? C::TILE : 0));
+          bulk_load(smem_u32(ring) + stage * STAGE_BYTES, in + base, C::TILE_BYTES, bar);
+          if(with_flags) bulk_load(smem_u32(ring) + stage * STAGE_BYTES + C::TILE_BYTES, flags + base, C::TILE, bar);
         }
       } else {
         // ragged last tile: guarded copy, zero fill
-        A* dst = reinterpret_cast<A*>(ring + (size_t)stage * C::TILE_BYTES);
+        A* dst = reinterpret_cast<A*>(ring + (size_t)stage * STAGE_BYTES);
         for(int e = lane; e < C::TILE; e += 32) dst[e] = (base + e < n) ? in[base + e] : A(0);
+        if(MODE == MODE_FLAGS && flags_in_ring) {
+          unsigned char* fdst = ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES;
+          for(int e = lane; e < C::TILE; e += 32) fdst[e] = (base + e < n) ? flags[base + e] : 0;
+        }
         __syncwarp();
         if(lane == 0) mbar_arrive(bar);
       }
@@ -688,9 +719,11 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         const bool full_tile = base + C::TILE <= n;
         A v[K][VEC];
         unsigned hf[K];
-        tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);
+        const bool ring_flags = MODE == MODE_FLAGS && flags_in_ring;
+        if(!ring_flags) tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);  // flag loads fly while we wait
         mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / WS_STAGES) & 1u);
-        tile_load_smem<A, K>(v, ring + (size_t)stage * C::TILE_BYTES + (size_t)warp * K * 512);
+        if(ring_flags) tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
+        tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
         A carry_in[K];
         bool open[K];
         A warp_agg;
@@ -721,9 +754,11 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         const size_t wbase = (size_t)tile * C::TILE + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
         A v[K][VEC];
         unsigned hf[K];
-        tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);
+        const bool ring_flags = MODE == MODE_FLAGS && flags_in_ring;
+        if(!ring_flags) tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);  // flag loads fly while we wait
         mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / WS_STAGES) & 1u);
-        tile_load_smem<A, K>(v, ring + (size_t)stage * C::TILE_BYTES + (size_t)warp * K * 512);
+        if(ring_flags) tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
+        tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
         A agg;
         bool has_head;
         warp_reduce_rows<A, MODE, K>(v, hf, agg, has_head);
@@ -744,8 +779,11 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         const bool full_tile = base + C::TILE <= n;
         A v[K][VEC];
         unsigned hf[K];
-        tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);
-        tile_load_smem<A, K>(v, ring + (size_t)stage * C::TILE_BYTES + (size_t)warp * K * 512);
+        if(MODE == MODE_FLAGS && flags_in_ring)
+          tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
+        else
+          tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);
+        tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
         A carry_in[K];
         bool open[K];
         A warp_agg;
@@ -781,17 +819,21 @@ int resident_ctas_per_sm(Kern kern, int threads, size_t smem) {
   return nb;
 }
 
+// rows per worker warp: 8 (64 KB tiles); 6 with explicit flags so that 3 stages of data + flag bytes fit in 227 KB
+template <int MODE> struct ws_rows { static constexpr int K = MODE == MODE_FLAGS ? (WS_K * 3) / 4 : WS_K; };
+
 template <typename A, int MODE>
 int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* flags,
     const A* seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, size_t tiles) {
-  using C = TileCfg<A, WS_NW, WS_K>;
-  constexpr size_t smem = (size_t)WS_STAGES * C::TILE_BYTES;
-  static const int per_sm = resident_ctas_per_sm(scan_ws_kernel<A, MODE>, WS_THREADS, smem);
+  constexpr int K = ws_rows<MODE>::K;
+  constexpr size_t smem = (size_t)WS_STAGES * ws_stage_bytes<A, MODE, K>();
+  static const int per_sm = resident_ctas_per_sm(scan_ws_kernel<A, MODE, K>, WS_THREADS, smem);
   if(per_sm <= 0) return SB_ERR_WORKSPACE;
   size_t grid = (size_t)ctx->sm_count * per_sm;
   if(grid > tiles) grid = tiles;
-  scan_ws_kernel<A, MODE><<<(unsigned)grid, WS_THREADS, smem, ctx->stream>>>(in, out, n, exclusive, seg_len, seg_mask, flags, seed, desc,
-      epoch, use_lookback, (long long)tiles);
+  const int flags_in_ring = (MODE == MODE_FLAGS && sb::aligned_to(flags, 16)) ? 1 : 0;  // TMA needs 16-byte aligned sources
+  scan_ws_kernel<A, MODE, K><<<(unsigned)grid, WS_THREADS, smem, ctx->stream>>>(in, out, n, exclusive, seg_len, seg_mask, flags, seed, desc,
+      epoch, use_lookback, (long long)tiles, flags_in_ring);
   return SB_OK;
 }
 
@@ -806,7 +848,8 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
 
   // persistent kernel for 16-byte aligned buffers with at least a few tiles; ticketed kernel otherwise
   const bool aligned = sb::aligned_to(in, 16) && sb::aligned_to(out, 16);
-  const size_t ws_tile = TileCfg<A, WS_NW, WS_K>::TILE, simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
+  const size_t ws_tile = mode == MODE_FLAGS ? TileCfg<A, WS_NW, ws_rows<MODE_FLAGS>::K>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
+  const size_t simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
   const bool use_ws = aligned && n >= 4 * ws_tile;
   const size_t tile = use_ws ? ws_tile : simple_tile;
   const size_t tiles = (n + tile - 1) / tile;

@@ -6,14 +6,19 @@
 // `acc[gid] = scratch[0]` for lid == 0.  Layout contract: :112-119 (head = sum, rest untouched).
 //
 // B200 design: HBM-bound stream, algorithmic bytes N*s + (N/L)*s.
-//  - no shared memory and no barriers: a warp streams "super-rows" of U=4 rows x 32 lanes x 16 B
+//  - no shared memory and no barriers: a warp streams "super-rows" of 4 rows x 32 lanes x 16 B
 //    (2 KB, four 128-bit loads in flight per lane, 128 KB per resident SM);
-//  - a segment is reduced with xor-shuffles over exactly the lanes that hold it
-//    (L <= 2 KB / s ... sub-warp groups; larger L ... register accumulation over super-rows then
-//    one warp reduce);
-//  - the head is rewritten by the lane that owns it (8..2 B scattered stores, one per segment).
-//  - grid = sm_count x 8 CTAs of 256 threads, warp-granular grid-stride so that a CTA reads
-//    16 KB contiguous per iteration.
+//  - the segment SHAPE is a template parameter (lanes per segment 1..32, two rows, four rows), so
+//    every instantiation is a straight-line loop body without guards; only the last, partial
+//    super-row takes the guarded path.  The first version decided the shape at run time inside
+//    the loop and sat at 69 % issue-slot utilisation for L=64 (profiles/r01_ncu_summary.txt);
+//  - a segment is summed by xor-shuffles over exactly the lanes that hold it; when a segment is one
+//    row, 64-bit / fp types sum the four rows of a super-row with 6 shuffles instead of 20
+//    (warp_sum4), 32-bit integers use redux.sync;
+//  - the head is rewritten by the lane that owns it (one scattered store per segment);
+//  - segments longer than a super-row accumulate in registers over their super-rows first;
+//  - grid = sm_count x 8 CTAs of 256 threads, warp-granular grid-stride: a CTA reads 16 KB
+//    contiguous per iteration.
 // A generic warp-per-segment kernel covers everything else (L not a power of two, L < 16 B,
 // unaligned buffers); it sums exactly the subset of a segment the reference's halving tree
 // reaches (oracle/sb_oracle.c: ref_tree_member).
@@ -22,15 +27,17 @@
 namespace {
 
 constexpr int SR_NT = 256;
-constexpr int SR_U = 4;
 constexpr int SR_CTAS_PER_SM = 8;
 
 template <typename A> struct acc_of { using type = A; };
 template <> struct acc_of<uint16_t> { using type = uint32_t; };
 
-template <typename Acc>
-__device__ __forceinline__ Acc group_sum(Acc s, int lanes) {
-  for(int d = lanes >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(SB_FULL_MASK, s, d);
+// sum over aligned groups of LANES lanes (compile-time), result in every lane of the group
+template <typename Acc, int LANES>
+__device__ __forceinline__ Acc group_sum(Acc s) {
+  if(LANES == 32) return sb::warp_sum<Acc>(s);
+#pragma unroll
+  for(int d = LANES >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(SB_FULL_MASK, s, d);
   return s;
 }
 
@@ -63,88 +70,136 @@ __device__ __forceinline__ Acc warp_sum2(Acc a0, Acc a1, int lane) {
   return k;
 }
 
-template <typename A, int NT, int U>
-__global__ void __launch_bounds__(NT) segreduce_pow2_kernel(A* buf, size_t n, size_t seg_len) {
+// SHAPE: 1..32 = lanes per segment (segment <= one row), 64 = segment is two rows, 128 = segment is a super-row
+// `row0` points at lane 0 of row 0 of the super-row; valid_rows (GUARDED only) = rows that exist.
+template <typename A, bool GUARDED>
+__device__ __forceinline__ void load_superrow(sb::Vec<A> (&t)[4], const A* row0, int lane, int valid_rows) {
+  constexpr int VEC = 16 / sizeof(A);
+  constexpr int ROW = 32 * VEC;
+  const A* p = row0 + lane * VEC;
+#pragma unroll
+  for(int u = 0; u < 4; ++u)
+    if(!GUARDED || u < valid_rows) t[u] = sb::ldg_stream<A>(p + u * ROW);
+}
+
+template <typename A, int SHAPE, bool GUARDED>
+__device__ __forceinline__ void reduce_superrow(const sb::Vec<A> (&t)[4], A* row0, int lane, int valid_rows) {
   using Acc = typename acc_of<A>::type;
   constexpr int VEC = 16 / sizeof(A);
-  constexpr size_t ROW = 32 * VEC;
-  constexpr size_t SUPER = U * ROW;
-  static_assert(U == 4, "the two-rows-per-segment case is written for U == 4");
-  const int lane = threadIdx.x & 31;
-  const size_t gw = (size_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-  const size_t nw = (size_t)gridDim.x * (NT / 32);
-
-  if(seg_len <= SUPER) {
-    const size_t nsuper = (n + SUPER - 1) / SUPER;
-    for(size_t sr = gw; sr < nsuper; sr += nw) {
-      const size_t base = sr * SUPER + (size_t)lane * VEC;
-      sb::Vec<A> t[U];
-      bool valid[U];
+  constexpr int ROW = 32 * VEC;
+  A* p = row0 + lane * VEC;
+  Acc s[4];
 #pragma unroll
-      for(int u = 0; u < U; ++u) {
-        const size_t idx = base + u * ROW;
-        valid[u] = idx < n;  // n % VEC == 0, vectors are entirely inside or outside
-        if(valid[u]) t[u] = sb::ldg_stream<A>(buf + idx);
-      }
-      Acc s[U];
+  for(int u = 0; u < 4; ++u) {
+    s[u] = Acc(0);
+    if(!GUARDED || u < valid_rows) {
 #pragma unroll
-      for(int u = 0; u < U; ++u) {
-        s[u] = Acc(0);
-        if(valid[u]) {
+      for(int c = 0; c < VEC; ++c) s[u] += t[u].v[c];
+    }
+  }
+  if(SHAPE == 32 && !sb::has_redux<Acc>::value) {
+    const Acc r = warp_sum4<Acc>(s[0], s[1], s[2], s[3], lane);
+    const int u = lane >> 3;
+    if((lane & 7) == 0 && (!GUARDED || u < valid_rows)) row0[u * ROW] = (A)r;
+  } else if(SHAPE <= 32) {
 #pragma unroll
-          for(int c = 0; c < VEC; ++c) s[u] += t[u].v[c];
-        }
-      }
-      const size_t sr_base = sr * SUPER;
-      if(seg_len == ROW && !sb::has_redux<Acc>::value) {
-        // one row per segment: four warp sums at once (64-bit / floating-point shuffles are the cost here;
-        // 32-bit integers use one redux.sync per sum instead)
-        const Acc t4 = warp_sum4<Acc>(s[0], s[1], s[2], s[3], lane);
-        const int u = lane >> 3;
-        if((lane & 7) == 0 && sr_base + u * ROW < n) buf[sr_base + u * ROW] = (A)t4;
-      } else if(seg_len <= ROW) {
-        const int lps = (int)(seg_len / VEC);  // lanes per segment, power of two in [1, 32]
-#pragma unroll
-        for(int u = 0; u < U; ++u) {
-          s[u] = group_sum<Acc>(s[u], lps);
-          if(valid[u] && (lane & (lps - 1)) == 0) buf[base + u * ROW] = (A)s[u];
-        }
-      } else if(seg_len == 2 * ROW && !sb::has_redux<Acc>::value) {
-        const Acc t2 = warp_sum2<Acc>(s[0] + s[1], s[2] + s[3], lane);
-        const int u = lane >> 4;
-        if((lane & 15) == 0 && sr_base + u * 2 * ROW < n) buf[sr_base + u * 2 * ROW] = (A)t2;
-      } else if(seg_len == 2 * ROW) {
-        const Acc a = sb::warp_sum<Acc>(s[0] + s[1]), b = sb::warp_sum<Acc>(s[2] + s[3]);
-        if(lane == 0) {
-          if(valid[0]) buf[base] = (A)a;
-          if(valid[2]) buf[base + 2 * ROW] = (A)b;
-        }
-      } else {  // seg_len == SUPER
-        Acc a = sb::warp_sum<Acc>((s[0] + s[1]) + (s[2] + s[3]));
-        if(lane == 0 && valid[0]) buf[base] = (A)a;
+    for(int u = 0; u < 4; ++u) {
+      const Acc r = group_sum<Acc, SHAPE>(s[u]);
+      if((lane & (SHAPE - 1)) == 0 && (!GUARDED || u < valid_rows)) p[u * ROW] = (A)r;
+    }
+  } else if(SHAPE == 64) {
+    if(!sb::has_redux<Acc>::value) {
+      const Acc r = warp_sum2<Acc>(s[0] + s[1], s[2] + s[3], lane);
+      const int u = lane >> 4;
+      if((lane & 15) == 0 && (!GUARDED || 2 * u < valid_rows)) row0[u * 2 * ROW] = (A)r;
+    } else {
+      const Acc a = sb::warp_sum<Acc>(s[0] + s[1]), b = sb::warp_sum<Acc>(s[2] + s[3]);
+      if(lane == 0) {
+        row0[0] = (A)a;
+        if(!GUARDED || valid_rows > 2) row0[2 * ROW] = (A)b;
       }
     }
   } else {
-    const size_t nseg = n / seg_len;
-    const size_t per = seg_len / SUPER;
-    for(size_t seg = gw; seg < nseg; seg += nw) {
-      A* p = buf + seg * seg_len + (size_t)lane * VEC;
-      Acc a[U];
+    const Acc a = sb::warp_sum<Acc>((s[0] + s[1]) + (s[2] + s[3]));
+    if(lane == 0) row0[0] = (A)a;
+  }
+}
+
+template <typename A, int NT, int SHAPE>
+__global__ void __launch_bounds__(NT) segreduce_rows_kernel(A* buf, size_t n) {
+  constexpr int VEC = 16 / sizeof(A);
+  constexpr size_t ROW = 32 * VEC;
+  constexpr size_t SUPER = 4 * ROW;
+  const int lane = threadIdx.x & 31;
+  const size_t gw = (size_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  const size_t nw = (size_t)gridDim.x * (NT / 32);
+  const size_t full = n / SUPER;
+  A* row0 = buf + gw * SUPER;
+  const size_t step = nw * SUPER;
+  sb::Vec<A> cur[4];
+  // 64-bit types with short segments spend long in the shuffle chains: keep the loads of the warp's
+  // next super-row in flight meanwhile (measured: f64 L=64 4.35 -> 5.08 TB/s; the extra registers
+  // cost occupancy and lose 5-12 % for 32-bit types and for L >= 256, so those stay unpipelined)
+  constexpr bool PREFETCH = sizeof(A) == 8 && SHAPE <= 64;
+  if(PREFETCH) {
+    sb::Vec<A> nxt[4];
+    if(gw < full) load_superrow<A, false>(cur, row0, lane, 4);
+    for(size_t sr = gw; sr < full; sr += nw, row0 += step) {
+      const bool more = sr + nw < full;
+      if(more) load_superrow<A, false>(nxt, row0 + step, lane, 4);
+      reduce_superrow<A, SHAPE, false>(cur, row0, lane, 4);
+      if(more) {
 #pragma unroll
-      for(int u = 0; u < U; ++u) a[u] = Acc(0);
-      for(size_t k = 0; k < per; ++k) {
-        sb::Vec<A> t[U];
-#pragma unroll
-        for(int u = 0; u < U; ++u) t[u] = sb::ldg_stream<A>(p + k * SUPER + u * ROW);
-#pragma unroll
-        for(int u = 0; u < U; ++u) {
-#pragma unroll
-          for(int c = 0; c < VEC; ++c) a[u] += t[u].v[c];
-        }
+        for(int u = 0; u < 4; ++u) cur[u] = nxt[u];
       }
-      Acc total = sb::warp_sum<Acc>((a[0] + a[1]) + (a[2] + a[3]));
-      if(lane == 0) buf[seg * seg_len] = (A)total;
     }
+  } else {
+    for(size_t sr = gw; sr < full; sr += nw, row0 += step) {
+      load_superrow<A, false>(cur, row0, lane, 4);
+      reduce_superrow<A, SHAPE, false>(cur, row0, lane, 4);
+    }
+  }
+  // partial last super-row (n is a multiple of the row length here, so whole rows remain)
+  const size_t rest = n - full * SUPER;
+  if(rest && gw == full % nw) {
+    const int valid_rows = (int)(rest / ROW);
+    load_superrow<A, true>(cur, buf + full * SUPER, lane, valid_rows);
+    reduce_superrow<A, SHAPE, true>(cur, buf + full * SUPER, lane, valid_rows);
+  }
+}
+
+// rows of a partial super-row may themselves be partial when a segment is shorter than a row:
+// such tails are left to the generic kernel (see segreduce_impl: the row kernel gets a multiple of ROW)
+
+// segments longer than a super-row: one warp per segment, register accumulation
+template <typename A, int NT>
+__global__ void __launch_bounds__(NT) segreduce_long_kernel(A* buf, size_t n, size_t seg_len) {
+  using Acc = typename acc_of<A>::type;
+  constexpr int VEC = 16 / sizeof(A);
+  constexpr size_t ROW = 32 * VEC;
+  constexpr size_t SUPER = 4 * ROW;
+  const int lane = threadIdx.x & 31;
+  const size_t gw = (size_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  const size_t nw = (size_t)gridDim.x * (NT / 32);
+  const size_t nseg = n / seg_len;
+  const size_t per = seg_len / SUPER;
+  for(size_t seg = gw; seg < nseg; seg += nw) {
+    A* p = buf + seg * seg_len + (size_t)lane * VEC;
+    Acc a[4];
+#pragma unroll
+    for(int u = 0; u < 4; ++u) a[u] = Acc(0);
+    for(size_t k = 0; k < per; ++k, p += SUPER) {
+      sb::Vec<A> t[4];
+#pragma unroll
+      for(int u = 0; u < 4; ++u) t[u] = sb::ldg_stream<A>(p + u * ROW);
+#pragma unroll
+      for(int u = 0; u < 4; ++u) {
+#pragma unroll
+        for(int c = 0; c < VEC; ++c) a[u] += t[u].v[c];
+      }
+    }
+    const Acc total = sb::warp_sum<Acc>((a[0] + a[1]) + (a[2] + a[3]));
+    if(lane == 0) buf[seg * seg_len] = (A)total;
   }
 }
 
@@ -175,6 +230,11 @@ __global__ void __launch_bounds__(NT) segreduce_generic_kernel(A* buf, size_t n,
   }
 }
 
+template <typename A, int SHAPE>
+void launch_rows(sb_ctx* ctx, A* buf, size_t n, size_t blocks) {
+  segreduce_rows_kernel<A, SR_NT, SHAPE><<<(unsigned)blocks, SR_NT, 0, ctx->stream>>>(buf, n);
+}
+
 template <typename T>
 int segreduce_impl(sb_ctx* ctx, T* inout, size_t n, size_t seg_len) {
   using A = typename sb_arith<T>::type;
@@ -183,22 +243,46 @@ int segreduce_impl(sb_ctx* ctx, T* inout, size_t n, size_t seg_len) {
   if(!sb::aligned_to(inout, sizeof(T))) return SB_ERR_MISALIGNED;
   if(n == 0) return SB_OK;
   sb_device_guard guard(ctx->device);
-  constexpr int VEC = 16 / sizeof(T);
+  constexpr size_t VEC = 16 / sizeof(T);
+  constexpr size_t ROW = 32 * VEC, SUPER = 4 * ROW;
+  constexpr size_t WPB = SR_NT / 32;
   A* buf = reinterpret_cast<A*>(inout);
   const bool pow2 = sb::is_pow2(seg_len);
   const size_t max_blocks = (size_t)ctx->sm_count * SR_CTAS_PER_SM;
-  if(pow2 && seg_len >= (size_t)VEC && sb::aligned_to(inout, 16)) {
-    const size_t super = (size_t)SR_U * 32 * VEC;
-    const size_t tasks = seg_len <= super ? (n + super - 1) / super : n / seg_len;
-    size_t blocks = (tasks + SR_NT / 32 - 1) / (SR_NT / 32);
-    if(blocks > max_blocks) blocks = max_blocks;
-    segreduce_pow2_kernel<A, SR_NT, SR_U><<<(unsigned)blocks, SR_NT, 0, ctx->stream>>>(buf, n, seg_len);
-  } else {
-    const size_t tasks = n / seg_len;
-    size_t blocks = (tasks + SR_NT / 32 - 1) / (SR_NT / 32);
-    if(blocks > max_blocks) blocks = max_blocks;
-    segreduce_generic_kernel<A, SR_NT><<<(unsigned)blocks, SR_NT, 0, ctx->stream>>>(buf, n, seg_len, pow2 ? 1 : 0);
+  auto blocks_for = [&](size_t tasks) {
+    size_t b = (tasks + WPB - 1) / WPB;
+    return b > max_blocks ? max_blocks : (b ? b : 1);
+  };
+  if(pow2 && seg_len >= VEC && sb::aligned_to(inout, 16)) {
+    if(seg_len > SUPER) {
+      segreduce_long_kernel<A, SR_NT><<<(unsigned)blocks_for(n / seg_len), SR_NT, 0, ctx->stream>>>(buf, n, seg_len);
+      SB_CHECK_LAUNCH(ctx);
+      return SB_OK;
+    }
+    // the row kernel takes whole rows; a tail shorter than a row (only possible when seg_len < ROW) goes generic
+    const size_t n_rows = (n / ROW) * ROW;
+    if(n_rows) {
+      const size_t blocks = blocks_for((n_rows + SUPER - 1) / SUPER);
+      const size_t lps = seg_len / VEC;  // lanes per segment if <= 32, else 64 / 128 = two / four rows
+      switch(lps) {
+      case 1: launch_rows<A, 1>(ctx, buf, n_rows, blocks); break;
+      case 2: launch_rows<A, 2>(ctx, buf, n_rows, blocks); break;
+      case 4: launch_rows<A, 4>(ctx, buf, n_rows, blocks); break;
+      case 8: launch_rows<A, 8>(ctx, buf, n_rows, blocks); break;
+      case 16: launch_rows<A, 16>(ctx, buf, n_rows, blocks); break;
+      case 32: launch_rows<A, 32>(ctx, buf, n_rows, blocks); break;
+      case 64: launch_rows<A, 64>(ctx, buf, n_rows, blocks); break;
+      default: launch_rows<A, 128>(ctx, buf, n_rows, blocks); break;
+      }
+      SB_CHECK_LAUNCH(ctx);
+    }
+    if(n_rows < n) {
+      segreduce_generic_kernel<A, SR_NT><<<(unsigned)blocks_for((n - n_rows) / seg_len), SR_NT, 0, ctx->stream>>>(buf + n_rows, n - n_rows, seg_len, 1);
+      SB_CHECK_LAUNCH(ctx);
+    }
+    return SB_OK;
   }
+  segreduce_generic_kernel<A, SR_NT><<<(unsigned)blocks_for(n / seg_len), SR_NT, 0, ctx->stream>>>(buf, n, seg_len, pow2 ? 1 : 0);
   SB_CHECK_LAUNCH(ctx);
   return SB_OK;
 }

@@ -447,3 +447,24 @@ def test_config4_segreduce_fp64_2p29(ctx, L):
     step = 1 << 16
     for s in range(0, v.shape[0], step):
         assert torch.equal(v[s:s + step], base[s:s + step] + off)
+
+
+@pytest.mark.parametrize("t", ["i32", "f64"])
+def test_host_api_chunked_pipeline(ctx, O, t):
+    """Arrays above 64 MiB are processed in chunks (upload k overlaps download k-1); a global scan
+    carries its running total between chunks as a device-resident seed."""
+    n = (1 << 25) + 4096 * 3 + (0 if t == "i32" else 8)
+    hx = rand_input(t, n)
+    res = np.empty_like(hx)
+    ctx.host_scan(hx, res)
+    assert_close(t, res, O.scan(t, hx), n, "chunked inclusive")
+    ctx.host_scan(hx, res, exclusive=True)
+    assert_close(t, res, O.scan(t, hx, True), n, "chunked exclusive")
+    ctx.host_scan(hx, res, exclusive=True, group_len=1000)
+    assert_close(t, res, O.scan(t, hx, True, 1000), n, "chunked group 1000")
+    m = (n // 256) * 256
+    buf = hx[:m].copy()
+    ctx.host_segreduce(buf, 256)
+    assert_close(t, buf, O.segreduce(t, hx[:m], 256), m, "chunked segreduce")
+    ctx.host_segscan(hx, res, seg_len=4096)
+    assert_close(t, res, O.scan(t, hx, False, 4096), n, "chunked segscan")
