@@ -674,14 +674,8 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
           if(with_flags) bulk_load(smem_u32(ring) + stage * STAGE_BYTES + C::TILE_BYTES, flags + base, C::TILE, bar);
         }
       } else {
-        // ragged last tile: guarded copy, zero fill
-        A* dst = reinterpret_cast<A*>(ring + (size_t)stage * STAGE_BYTES);
-        for(int e = lane; e < C::TILE; e += 32) dst[e] = (base + e < n) ? in[base + e] : A(0);
-        if(MODE == MODE_FLAGS && flags_in_ring) {
-          unsigned char* fdst = ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES;
-          for(int e = lane; e < C::TILE; e += 32) fdst[e] = (base + e < n) ? flags[base + e] : 0;
-        }
-        __syncwarp();
+        // ragged last tile: nothing is staged (the workers read it from global memory with guards);
+        // the arrive only completes the barrier phase the workers wait on
         if(lane == 0) mbar_arrive(bar);
       }
     }
@@ -719,11 +713,12 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         const bool full_tile = base + C::TILE <= n;
         A v[K][VEC];
         unsigned hf[K];
-        const bool ring_flags = MODE == MODE_FLAGS && flags_in_ring;
+        const bool ring_flags = MODE == MODE_FLAGS && flags_in_ring && full_tile;
         if(!ring_flags) tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);  // flag loads fly while we wait
         mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / WS_STAGES) & 1u);
         if(ring_flags) tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
-        tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
+        if(full_tile) tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
+        else tile_load_global<A, true, K>(v, in, wbase, false, n);  // ragged last tile
         A carry_in[K];
         bool open[K];
         A warp_agg;
@@ -752,13 +747,15 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         const int stage = (int)(it % WS_STAGES), slot = (int)(it % WS_NSLOT);
         const long long tile = (long long)blockIdx.x + it * G;
         const size_t wbase = (size_t)tile * C::TILE + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
+        const bool full_tile = (size_t)(tile + 1) * C::TILE <= n;
         A v[K][VEC];
         unsigned hf[K];
-        const bool ring_flags = MODE == MODE_FLAGS && flags_in_ring;
+        const bool ring_flags = MODE == MODE_FLAGS && flags_in_ring && full_tile;
         if(!ring_flags) tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);  // flag loads fly while we wait
         mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / WS_STAGES) & 1u);
         if(ring_flags) tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
-        tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
+        if(full_tile) tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
+        else tile_load_global<A, true, K>(v, in, wbase, false, n);  // ragged last tile
         A agg;
         bool has_head;
         warp_reduce_rows<A, MODE, K>(v, hf, agg, has_head);
@@ -779,11 +776,12 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         const bool full_tile = base + C::TILE <= n;
         A v[K][VEC];
         unsigned hf[K];
-        if(MODE == MODE_FLAGS && flags_in_ring)
+        if(MODE == MODE_FLAGS && flags_in_ring && full_tile)
           tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
         else
           tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);
-        tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
+        if(full_tile) tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
+        else tile_load_global<A, true, K>(v, in, wbase, false, n);  // ragged last tile
         A carry_in[K];
         bool open[K];
         A warp_agg;
