@@ -375,7 +375,11 @@ def cpu_reference(legs, sample_log2: int, steps: int, warmup: int):
     sec = sum(leg.values())
     step_bytes = sum(algorithmic_bytes(op, t, n) for op, t in legs)
     value = step_bytes / sec / 1e9
-    cpu = {"value": round(value, 3), "unit": "GB/s", "cores": threads, "kind": "reference" if have_ref else "port",
+    scan_legs = [f"{op}_{t}" for op, t in legs if op == "scan"]
+    legs_kind = {f"{op}_{t}": ("reference" if (op == "reduce" and have_ref) else "port") for op, t in legs}
+    cpu = {"value": round(value, 3), "unit": "GB/s", "cores": threads,
+           # "reference" only if EVERY leg ran the reference's own code; the prefix-sum legs never can (upstream has none)
+           "kind": "reference" if all(k == "reference" for k in legs_kind.values()) else "port", "legs_kind": legs_kind,
            "sample": f"the same {len(legs)} legs at 2^{sample_log2} elements (bounded sample; GB/s is size-independent); "
                      + ("reduction legs: unmodified reference pattern/reduction.cpp on the host SYCL shim (oracle/_ref, OpenMP over work-groups), its own run-time; "
                         if have_ref else "reduction legs: oracle restatement of the reference tree (OpenMP); ")
