@@ -808,6 +808,108 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
   }
 }
 
+// ---- kernel 3: independent tiles (every tile starts on a segment head): no descriptors, no look-back ------
+// Same ring and worker code as the single-phase path above, but tiles are handed out IN ORDER by an
+// atomic ticket, taken by the producer whenever a ring stage frees up, which keeps the DRAM access
+// front compact and ordered.  A persistent copy kernel with static grid-stride assignment measures
+// 5.97 TB/s on B200, the same kernel with ticketed chunks 6.95 TB/s (profiles/r01_stream_probe.txt);
+// this path gained 4-10 % (f32 L=256: 6.1 -> 6.76 TB/s).  With a look-back the ticketed assignment
+// LOSES (2.3-5.0 instead of 5.6-5.8 TB/s): a CTA gets a random position in every round, whereas the
+// static round-robin settles into a stable stagger in which the aggregates a tile needs are almost
+// always published before it asks — so the look-back kernel above keeps static assignment.
+constexpr int WS_TILE_IDS = 8;  // ring of tile ids handed from the producer to the workers
+
+template <typename A, int MODE, int K>
+__global__ void __launch_bounds__((WS_NW + 1) * 32, SB_WS_MINB)
+scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
+    long long num_tiles, int flags_in_ring, unsigned long long* ticket, unsigned long long ticket_base) {
+  using C = TileCfg<A, WS_NW, K>;
+  constexpr int VEC = C::VEC;
+  constexpr int NW = WS_NW;
+  constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K>();
+  extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x STAGE_BYTES
+  __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES], agg_bar[WS_NSLOT];
+  __shared__ A s_wagg[WS_NSLOT][NW];
+  __shared__ int s_wflag[WS_NSLOT][NW];
+  __shared__ int s_tile_id[WS_TILE_IDS];  // tile of the CTA's i-th iteration, -1 = no more tiles
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if(threadIdx.x == 0) {
+#pragma unroll
+    for(int s = 0; s < WS_STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), NW);
+    }
+#pragma unroll
+    for(int s = 0; s < WS_NSLOT; ++s) mbar_init(smem_u32(&agg_bar[s]), NW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if(warp == NW) {
+    // ===== producer: draws tile tickets, TMA bulk loads into the ring =====
+    if(lane != 0) return;
+    for(int i = 0;; ++i) {
+      const int stage = i % WS_STAGES;
+      if(i >= WS_STAGES) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)((i / WS_STAGES) - 1) & 1u);
+      const long long tile = (long long)(atomicAdd(ticket, 1ull) - ticket_base);
+      const uint32_t bar = smem_u32(&full_bar[stage]);
+      if(tile >= num_tiles) {
+        s_tile_id[i % WS_TILE_IDS] = -1;
+        mbar_arrive(bar);  // releases the workers; they read the -1 and leave
+        break;
+      }
+      s_tile_id[i % WS_TILE_IDS] = (int)tile;
+      const size_t base = (size_t)tile * C::TILE;
+      if(base + C::TILE <= n) {
+        const bool with_flags = MODE == MODE_FLAGS && flags_in_ring;
+        mbar_expect_tx(bar, C::TILE_BYTES + (with_flags ? C::TILE : 0));
+        bulk_load(smem_u32(ring) + stage * STAGE_BYTES, in + base, C::TILE_BYTES, bar);
+        if(with_flags) bulk_load(smem_u32(ring) + stage * STAGE_BYTES + C::TILE_BYTES, flags + base, C::TILE, bar);
+      } else {
+        mbar_arrive(bar);  // ragged last tile: read from global memory by the workers
+      }
+    }
+    return;
+  }
+  // ===== workers =====
+  for(int it = 0;; ++it) {
+    const int stage = it % WS_STAGES, slot = it % WS_NSLOT;
+    mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / WS_STAGES) & 1u);
+    const int tile = s_tile_id[it % WS_TILE_IDS];
+    if(tile < 0) break;
+    const size_t base = (size_t)tile * C::TILE;
+    const size_t wbase = base + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
+    const bool full_tile = base + C::TILE <= n;
+    A v[K][VEC];
+    unsigned hf[K];
+    if(MODE == MODE_FLAGS && flags_in_ring && full_tile)
+      tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
+    else
+      tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);
+    if(full_tile) tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
+    else tile_load_global<A, true, K>(v, in, wbase, false, n);
+    A carry_in[K];
+    bool open[K];
+    A warp_agg;
+    bool warp_has_head;
+    tile_pass1<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+    if(lane == 0) {
+      mbar_arrive(smem_u32(&empty_bar[stage]));  // the tile lives in registers now
+      s_wagg[slot][warp] = warp_agg;
+      s_wflag[slot][warp] = warp_has_head ? 1 : 0;
+      mbar_arrive(smem_u32(&agg_bar[slot]));
+    }
+    A my_prefix = A(0), tile_agg;
+    bool my_open = true, tile_has_head;
+    if(!(MODE != MODE_PLAIN && (sb::shfl_idx(hf[0], 0) & 1u))) {  // a warp chunk that starts on a head needs no one
+      mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(it / WS_NSLOT) & 1u);
+      combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], warp, my_prefix, my_open, tile_agg, tile_has_head);
+    }
+    tile_pass2_store<A, MODE, true, K>(v, hf, carry_in, open, my_prefix, wbase, full_tile, n, out, exclusive);
+  }
+}
+
 // co-resident CTAs per SM of a persistent kernel instantiation (queried once per process)
 template <typename Kern>
 int resident_ctas_per_sm(Kern kern, int threads, size_t smem) {
@@ -829,9 +931,26 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
   if(per_sm <= 0) return SB_ERR_WORKSPACE;
   size_t grid = (size_t)ctx->sm_count * per_sm;
   if(grid > tiles) grid = tiles;
-  const int flags_in_ring = (MODE == MODE_FLAGS && sb::aligned_to(flags, 16)) ? 1 : 0;  // TMA needs 16-byte aligned sources
-  scan_ws_kernel<A, MODE, K><<<(unsigned)grid, WS_THREADS, smem, ctx->stream>>>(in, out, n, exclusive, seg_len, seg_mask, flags, seed, desc,
-      epoch, use_lookback, (long long)tiles, flags_in_ring);
+  int flags_in_ring = (MODE == MODE_FLAGS && sb::aligned_to(flags, 16)) ? 1 : 0;  // TMA needs 16-byte aligned sources
+  long long num_tiles = (long long)tiles;
+  if(!use_lookback) {
+    static const int ind_per_sm = resident_ctas_per_sm(scan_independent_kernel<A, MODE, K>, (WS_NW + 1) * 32, smem);
+    if(ind_per_sm <= 0) return SB_ERR_WORKSPACE;
+    size_t g = (size_t)ctx->sm_count * ind_per_sm;
+    if(g > tiles) g = tiles;
+    // every CTA's producer draws tickets until one is past the last tile: tiles + grid tickets per launch
+    const unsigned long long tbase = ctx->scan_ticket_base;
+    ctx->scan_ticket_base += tiles + g;
+    scan_independent_kernel<A, MODE, K><<<(unsigned)g, (WS_NW + 1) * 32, smem, ctx->stream>>>(in, out, n, exclusive, seg_len, seg_mask, flags,
+        num_tiles, flags_in_ring, ctx->scan_ticket, tbase);
+    return SB_OK;
+  }
+  // Cooperative launch: the runtime guarantees that all CTAs of the grid are co-resident (or refuses the
+  // launch) — the forward-progress condition of the static round-robin look-back.  No grid barrier is used.
+  void* args[] = {(void*)&in, (void*)&out, (void*)&n, (void*)&exclusive, (void*)&seg_len, (void*)&seg_mask, (void*)&flags, (void*)&seed,
+      (void*)&desc, (void*)&epoch, (void*)&use_lookback, (void*)&num_tiles, (void*)&flags_in_ring};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_ws_kernel<A, MODE, K>, dim3((unsigned)grid), dim3(WS_THREADS), args, smem, ctx->stream);
+  if(e != cudaSuccess) return (int)e;
   return SB_OK;
 }
 
