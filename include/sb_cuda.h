@@ -77,6 +77,10 @@ int sb_ctx_device_name(sb_ctx* ctx, char* buf, size_t buflen);
 int sb_ctx_sm_count(sb_ctx* ctx);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 uint64_t sb_ctx_launch_count(sb_ctx* ctx);
+/* on != 0: floating-point sb_reduce_* uses a fixed summation order (bit-reproducible run to run,
+ * about 3 % slower).  Default off: chunks are handed to CTAs in order of arrival.  Integer results
+ * and all scans are reproducible either way. */
+int sb_ctx_set_deterministic(sb_ctx* ctx, int on);
 /* Bytes of device scratch the ctx holds / that an op on n elements touches. */
 size_t sb_workspace_bytes(int op, int dtype, size_t n);
 

@@ -18,6 +18,7 @@ struct sb_ctx {
   bool own_stream = false;
   int sm_count = 0;
   uint64_t launches = 0;
+  bool deterministic = false;  // sb_ctx_set_deterministic: bit-reproducible floating-point reductions
 
   // reduce: per-block partials (8 B each) + completion ticket
   void* partials = nullptr;
@@ -98,6 +99,16 @@ __device__ __forceinline__ Vec<T> ldg_nc(const T* p) {
   asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return *reinterpret_cast<Vec<T>*>(&r);
 }
+// same, but `volatile`: the compiler keeps these loads in program order, i.e. a batch of them written
+// back to back is ISSUED back to back.  Without it nvcc sinks some loads next to their first use for
+// some element types (measured on the reduce kernel: int32 5.85 and fp64 5.6 TB/s against 6.9-7.05 for
+// fp32 / int64 with identical source), which halves the bytes in flight per thread.
+template <typename T>
+__device__ __forceinline__ Vec<T> ldg_nc_ordered(const T* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return *reinterpret_cast<Vec<T>*>(&r);
+}
 // streaming 128-bit load through the coherent path (buffer may be written by this kernel)
 template <typename T>
 __device__ __forceinline__ Vec<T> ldg_stream(const T* p) {
@@ -147,4 +158,5 @@ inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintp
 // workspace growth helpers (sb_ctx.cu)
 int sb_ctx_reserve_desc(sb_ctx* ctx, size_t count64, size_t count128);
 int sb_ctx_reserve_stage(sb_ctx* ctx, int which, size_t bytes);
+int sb_ctx_reserve_partials(sb_ctx* ctx, size_t slots);
 size_t sb_scan_tile_bytes();  // sb_scan.cu

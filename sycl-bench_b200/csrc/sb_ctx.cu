@@ -143,6 +143,12 @@ int sb_ctx_device_name(sb_ctx* ctx, char* buf, size_t buflen) {
   return SB_OK;
 }
 
+int sb_ctx_set_deterministic(sb_ctx* ctx, int on) {
+  if(!ctx) return SB_ERR_BAD_ARG;
+  ctx->deterministic = on != 0;
+  return SB_OK;
+}
+
 int sb_ctx_sm_count(sb_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t sb_ctx_launch_count(sb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -246,6 +252,23 @@ int sb_ctx_reserve_desc(sb_ctx* ctx, size_t count64, size_t count128) {
   int rc = grow(ctx, &ctx->desc64, &ctx->desc64_count, count64, 8);
   if(rc != SB_OK) return rc;
   return grow(ctx, &ctx->desc128, &ctx->desc128_count, count128, 16);
+}
+
+int sb_ctx_reserve_partials(sb_ctx* ctx, size_t slots) {
+  if(slots <= ctx->partials_slots) return SB_OK;
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if(e != cudaSuccess) return (int)e;
+  cudaFree(ctx->partials);
+  ctx->partials = nullptr;
+  ctx->partials_slots = 0;
+  const size_t cap = slots + slots / 4;
+  e = cudaMalloc(&ctx->partials, cap * 8);
+  if(e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return SB_ERR_WORKSPACE;
+  }
+  ctx->partials_slots = cap;
+  return SB_OK;
 }
 
 int sb_ctx_reserve_stage(sb_ctx* ctx, int which, size_t bytes) {

@@ -5,13 +5,26 @@
 // kernels of one element per work-item with a log2(L)-barrier shared-memory tree.
 //
 // B200 design: HBM-bound read-only stream (algorithmic bytes N*s + s).
-//  - persistent grid of sm_count * CTAS_PER_SM CTAs, grid-stride over chunks of NT*UNROLL 16-byte
-//    vectors; all UNROLL 128-bit loads of a thread are issued before the first add, so a resident
-//    SM keeps 2048 threads * 64 B = 128 KB in flight (B200 needs ~43 KB/SM to cover HBM latency).
-//  - loads are ld.global.nc.L1::no_allocate.v4 (streamed once, keep L1/L2 clean).
+//  - persistent grid of sm_count * 4 CTAs of 512 threads; the 32 KB chunks are handed out IN ORDER by
+//    an atomic ticket (the next ticket is drawn while the current chunk is in flight).  In-order
+//    hand-out keeps the DRAM access front compact: the same copy kernel measures 5.97 TB/s with a
+//    static grid-stride assignment and 6.95 TB/s with ticketed chunks (profiles/r01_stream_probe.txt).
+//    A flat grid (one chunk per CTA) orders the accesses as well but pays the block epilogue per
+//    chunk, which cost fp64 20 % (profiles/r01_ops_v6_flat_grids.jsonl).
+//  - all UNROLL 128-bit loads of a thread are issued before the first add
+//    (ld.global.nc.L1::no_allocate.v4: streamed once, keeps L1/L2 clean); a resident SM keeps
+//    2048 threads * 64 B = 128 KB in flight (B200 needs ~43 KB/SM to cover HBM latency).
 //  - warp stage: redux.sync.add for 32-bit integers, xor-shuffle tree for 64-bit / floating point.
 //  - block stage through 64 B of shared memory, one partial per CTA to the ctx scratch, and a
-//    last-block-done ticket sums the partials in index order: fixed order => deterministic fp.
+//    last-block-done ticket sums the partials in index order.  Chunks are ticketed, so WHICH chunks a
+//    CTA sums depends on timing: integer results are exact regardless; floating-point results are
+//    within the stated tolerance but not bit-reproducible run to run.  sb_ctx_set_deterministic(ctx, 1)
+//    selects the static chunk assignment instead: fixed summation order, bit-reproducible, ~3 % slower
+//    (i32 6.76 vs 6.97, f64 7.11 vs 7.25 TB/s).
+//  - the loads are `volatile` asm so that the batch is issued back to back; with plain asm nvcc sank
+//    part of the batch next to its first use for int32 and fp64 (5.85 / 5.6 TB/s).
+#include <cstdlib>
+
 #include "sb_common.cuh"
 
 namespace {
@@ -34,12 +47,14 @@ __device__ __forceinline__ A block_sum(A v, A* smem) {
   return r;  // valid in warp 0
 }
 
-template <typename A, int NT, int UNROLL>
+// tickets[0] = CTAs done, tickets[1] = next chunk
+template <typename A, int NT, int UNROLL, bool TICKETED>
 __global__ void __launch_bounds__(NT) reduce_kernel(const A* __restrict__ in, size_t n, A* __restrict__ partials,
-    unsigned int* __restrict__ ticket, A* __restrict__ out) {
+    unsigned int* __restrict__ tickets, A* __restrict__ out) {
   constexpr int VEC = 16 / sizeof(A);
   __shared__ A smem[NT / 32];
   __shared__ bool is_last;
+  __shared__ unsigned int s_chunk[2];
 
   // peel elements in front of the first 16-byte boundary
   size_t head = ((16 - (reinterpret_cast<uintptr_t>(in) & 15)) & 15) / sizeof(A);
@@ -52,14 +67,15 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const A* __restrict__ in, si
 #pragma unroll
   for(int u = 0; u < UNROLL; ++u) acc[u] = A(0);
 
-  constexpr size_t CHUNK = (size_t)NT * UNROLL;
-  const size_t stride = (size_t)gridDim.x * CHUNK;
-  for(size_t base = (size_t)blockIdx.x * CHUNK; base < nvec; base += stride) {
-    const size_t i0 = base + threadIdx.x;
-    if(base + CHUNK <= nvec) {
+  constexpr size_t CHUNK = (size_t)NT * UNROLL;  // vectors per chunk
+  const size_t nchunks = (nvec + CHUNK - 1) / CHUNK;
+
+  auto do_chunk = [&](size_t chunk) {
+    const size_t i0 = chunk * CHUNK + threadIdx.x;
+    if((chunk + 1) * CHUNK <= nvec) {
       sb::Vec<A> t[UNROLL];
 #pragma unroll
-      for(int u = 0; u < UNROLL; ++u) t[u] = sb::ldg_nc<A>(body + (i0 + (size_t)u * NT) * VEC);
+      for(int u = 0; u < UNROLL; ++u) t[u] = sb::ldg_nc_ordered<A>(body + (i0 + (size_t)u * NT) * VEC);
 #pragma unroll
       for(int u = 0; u < UNROLL; ++u) {
         A s = t[u].v[0];
@@ -80,6 +96,21 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const A* __restrict__ in, si
         }
       }
     }
+  };
+
+  if(TICKETED) {
+    // double-buffered ticket: the draw for the next chunk overlaps the loads of the current one
+    if(threadIdx.x == 0) s_chunk[0] = atomicAdd(tickets + 1, 1u);
+    __syncthreads();
+    for(int b = 0;; b ^= 1) {
+      const size_t chunk = s_chunk[b];
+      if(chunk >= nchunks) break;
+      if(threadIdx.x == 0) s_chunk[b ^ 1] = atomicAdd(tickets + 1, 1u);
+      do_chunk(chunk);
+      __syncthreads();
+    }
+  } else {
+    for(size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) do_chunk(chunk);
   }
   A v = acc[0];
 #pragma unroll
@@ -96,7 +127,7 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const A* __restrict__ in, si
   if(threadIdx.x == 0) {
     partials[blockIdx.x] = bs;
     __threadfence();
-    const unsigned int done = atomicAdd(ticket, 1u);
+    const unsigned int done = atomicAdd(tickets, 1u);
     is_last = (done == gridDim.x - 1);
   }
   __syncthreads();
@@ -108,7 +139,8 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const A* __restrict__ in, si
     A total = block_sum<A, NT>(p, smem);
     if(threadIdx.x == 0) {
       out[0] = total;
-      *ticket = 0u;  // ready for the next launch on this stream
+      tickets[0] = 0u;  // every CTA has drawn its last ticket and signed off: re-arm for the next launch
+      tickets[1] = 0u;
     }
   }
 }
@@ -121,13 +153,22 @@ int reduce_impl(sb_ctx* ctx, const T* in, size_t n, T* out) {
   sb_device_guard guard(ctx->device);
   constexpr int VEC = 16 / sizeof(T);
   const size_t chunk_elems = (size_t)RED_NT * RED_UNROLL * VEC;
-  size_t blocks = (n + chunk_elems - 1) / chunk_elems;
+  const size_t chunks = (n + chunk_elems - 1) / chunk_elems;
+  if(chunks >= 0xfffffff0ull) return SB_ERR_BAD_ARG;  // 32-bit chunk tickets: n below 2^47 bytes
+  size_t blocks = chunks;
   const size_t max_blocks = (size_t)ctx->sm_count * RED_CTAS_PER_SM;
   if(blocks > max_blocks) blocks = max_blocks;
   if(blocks < 1) blocks = 1;
   if(blocks > ctx->partials_slots) blocks = ctx->partials_slots;
-  reduce_kernel<A, RED_NT, RED_UNROLL><<<(unsigned)blocks, RED_NT, 0, ctx->stream>>>(
-      reinterpret_cast<const A*>(in), n, reinterpret_cast<A*>(ctx->partials), ctx->reduce_ticket, reinterpret_cast<A*>(out));
+  static const bool env_deterministic = getenv("SB_REDUCE_DETERMINISTIC") && getenv("SB_REDUCE_DETERMINISTIC")[0] == '1';
+  const bool deterministic = env_deterministic || ctx->deterministic;
+  const A* ain = reinterpret_cast<const A*>(in);
+  A* apart = reinterpret_cast<A*>(ctx->partials);
+  A* aout = reinterpret_cast<A*>(out);
+  if(deterministic)
+    reduce_kernel<A, RED_NT, RED_UNROLL, false><<<(unsigned)blocks, RED_NT, 0, ctx->stream>>>(ain, n, apart, ctx->reduce_ticket, aout);
+  else
+    reduce_kernel<A, RED_NT, RED_UNROLL, true><<<(unsigned)blocks, RED_NT, 0, ctx->stream>>>(ain, n, apart, ctx->reduce_ticket, aout);
   SB_CHECK_LAUNCH(ctx);
   return SB_OK;
 }

@@ -22,6 +22,8 @@
 // A generic warp-per-segment kernel covers everything else (L not a power of two, L < 16 B,
 // unaligned buffers); it sums exactly the subset of a segment the reference's halving tree
 // reaches (oracle/sb_oracle.c: ref_tree_member).
+#include <cstdlib>
+
 #include "sb_common.cuh"
 
 namespace {
@@ -262,8 +264,15 @@ int segreduce_impl(sb_ctx* ctx, T* inout, size_t n, size_t seg_len) {
     // the row kernel takes whole rows; a tail shorter than a row (only possible when seg_len < ROW) goes generic
     const size_t n_rows = (n / ROW) * ROW;
     if(n_rows) {
-      const size_t blocks = blocks_for((n_rows + SUPER - 1) / SUPER);
+      // FLAT grid (one super-row per warp, CTAs dispatched in order): in-order dispatch keeps the DRAM
+      // access front compact (profiles/r01_stream_probe.txt; L=256: 5.2 -> 5.5 TB/s i32, 5.9 -> 6.4 f64).
+      // Exception: 64-bit types with segments of at most two rows are bound by their shuffle chains and
+      // do better with the persistent, software-pipelined loop (f64 L=64: 4.78 flat, 4.98 persistent).
       const size_t lps = seg_len / VEC;  // lanes per segment if <= 32, else 64 / 128 = two / four rows
+      const bool persistent = sizeof(T) == 8 && lps <= 64;
+      size_t blocks = ((n_rows + SUPER - 1) / SUPER + WPB - 1) / WPB;
+      if(persistent) blocks = blocks_for((n_rows + SUPER - 1) / SUPER);
+      if(blocks > (size_t(1) << 24)) blocks = size_t(1) << 24;
       switch(lps) {
       case 1: launch_rows<A, 1>(ctx, buf, n_rows, blocks); break;
       case 2: launch_rows<A, 2>(ctx, buf, n_rows, blocks); break;

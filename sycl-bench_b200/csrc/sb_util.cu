@@ -92,8 +92,12 @@ __global__ void __launch_bounds__(UT_NT) check_iota_kernel(const A* __restrict__
 }
 
 size_t grid_for(sb_ctx* ctx, size_t work_items, size_t per_block) {
+  // flat grids: one chunk per CTA, dispatched in order (an ordered DRAM access front is worth ~15 % on
+  // B200 against a persistent grid-stride grid, profiles/r01_stream_probe.txt); the kernels still loop
+  // if the cap is ever hit
+  (void)ctx;
   size_t blocks = (work_items + per_block - 1) / per_block;
-  const size_t cap = (size_t)ctx->sm_count * 8;
+  const size_t cap = size_t(1) << 22;
   if(blocks > cap) blocks = cap;
   return blocks ? blocks : 1;
 }

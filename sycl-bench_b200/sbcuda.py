@@ -68,6 +68,7 @@ def lib() -> C.CDLL:
     L.sb_ctx_sync.argtypes = [vp]
     L.sb_ctx_device_name.argtypes = [vp, C.c_char_p, sz]
     L.sb_ctx_sm_count.argtypes = [vp]
+    L.sb_ctx_set_deterministic.argtypes = [vp, i]
     L.sb_ctx_launch_count.argtypes = [vp]
     L.sb_ctx_launch_count.restype = u64
     L.sb_workspace_bytes.argtypes = [i, i, sz]
@@ -152,6 +153,10 @@ class Context:
     # -- plumbing
     def sync(self) -> None:
         _check(lib().sb_ctx_sync(self._h))
+
+    def set_deterministic(self, on: bool) -> None:
+        """Bit-reproducible floating-point reductions (fixed summation order, ~3 % slower)."""
+        _check(lib().sb_ctx_set_deterministic(self._h, int(on)))
 
     def set_stream(self, stream: Optional[int]) -> None:
         _check(lib().sb_ctx_set_stream(self._h, stream))
