@@ -47,7 +47,8 @@ enum sb_status {
   SB_ERR_SEG_LEN = -4,     /* seg_len == 0, or n % seg_len != 0 where the reference asserts it */
   SB_ERR_NO_DEVICE = -5,   /* no CUDA device / device index out of range                       */
   SB_ERR_UNSUPPORTED = -6, /* device is not sm_100 (library is built for sm_100a only)         */
-  SB_ERR_TIMER = -7        /* sb_timer_end without sb_timer_begin                              */
+  SB_ERR_TIMER = -7,       /* sb_timer_end without sb_timer_begin                              */
+  SB_ERR_NCCL = -8         /* libnccl.so.2 could not be loaded, or an NCCL call failed         */
 };
 
 enum sb_dtype { SB_I16 = 0, SB_I32 = 1, SB_I64 = 2, SB_F32 = 3, SB_F64 = 4 };
@@ -187,6 +188,31 @@ int sb_host_reduce(sb_ctx*, int dtype, const void* h_in, size_t n, void* h_out);
 int sb_host_scan(sb_ctx*, int dtype, const void* h_in, void* h_out, size_t n, int exclusive, size_t group_len);
 int sb_host_segreduce(sb_ctx*, int dtype, void* h_inout, size_t n, size_t seg_len);
 int sb_host_segscan(sb_ctx*, int dtype, const void* h_in, void* h_out, size_t n, size_t seg_len, const uint8_t* h_head_flags, int exclusive);
+
+/* ---- sharded operations over the GPUs of one box (single process, NCCL over NVLink) ---------- */
+/* The reference is single-device; this is the multi-GPU path of BASELINE.json north_star: the input
+ * is sharded contiguously over ngpus devices, every rank reduces / scans its shard with the kernels
+ * above, and NCCL exchanges ONE element per rank: all-reduce(sum) for the reduction, all-gather of
+ * the shard totals for the scan's exclusive carry.  libnccl.so.2 is loaded lazily (dlopen), so the
+ * library has no NCCL dependency unless these calls are used.
+ *   rank 0 is `rank0` (its device, its stream: the harness's timer ctx); ranks 1.. get new ctxs on
+ *   the following devices.  in[r] / out[r] are device pointers on rank r's device, n[r] its shard size.
+ *   All work is asynchronous; sb_comm_join makes rank 0's stream wait for every other rank, so that
+ *   sb_timer_end / sb_ctx_sync on rank 0 cover the whole operation. */
+typedef struct sb_comm sb_comm;
+enum sb_scan_strategy {
+  SB_REDUCE_THEN_SCAN = 0, /* sb_reduce -> all-gather -> seeded sb_scan: 3 passes over a shard (default) */
+  SB_SCAN_THEN_CARRY = 1   /* sb_scan -> all-gather -> sb_carry_add: the 4-pass recipe, inclusive only */
+};
+int sb_comm_create(sb_ctx* rank0, int ngpus, sb_comm** out);
+int sb_comm_destroy(sb_comm* comm);
+int sb_comm_size(sb_comm* comm);
+sb_ctx* sb_comm_ctx(sb_comm* comm, int rank);
+int sb_comm_join(sb_comm* comm);
+/* out[r][0] = sum over ALL shards, on every rank */
+int sb_comm_reduce(sb_comm* comm, int dtype, const void* const* in, const size_t* n, void* const* out);
+/* out[r] = rank r's shard of the GLOBAL inclusive / exclusive scan */
+int sb_comm_scan(sb_comm* comm, int dtype, const void* const* in, void* const* out, const size_t* n, int exclusive, int strategy);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

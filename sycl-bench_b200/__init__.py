@@ -11,6 +11,7 @@ The directory name contains a hyphen (it is the reference's name), so it is impo
 """
 from .sbcuda import (  # noqa: F401
     DTYPES,
+    Comm,
     Context,
     SbError,
     lib,
@@ -18,4 +19,4 @@ from .sbcuda import (  # noqa: F401
     declared_symbols,
 )
 
-__all__ = ["DTYPES", "Context", "SbError", "lib", "lib_path", "declared_symbols"]
+__all__ = ["DTYPES", "Comm", "Context", "SbError", "lib", "lib_path", "declared_symbols"]

@@ -1,0 +1,261 @@
+// sb_comm_*: the sharded (multi-GPU) reduction and prefix sum of BASELINE.json north_star, driven from
+// one process: per-rank kernels of libsb_cuda + ONE tiny NCCL collective per operation.
+//
+//   reduction : sb_reduce per shard -> ncclAllReduce(sum) of one element per rank
+//   scan      : SB_REDUCE_THEN_SCAN  sb_reduce -> ncclAllGather of the shard totals -> sb_exclusive_carry
+//                                    -> sb_scan seeded with the carry                  (3 passes / shard)
+//               SB_SCAN_THEN_CARRY   sb_scan -> ncclAllGather -> sb_exclusive_carry -> sb_carry_add (4 passes)
+//
+// The reference has no multi-device code; nothing here replaces a reference function.  NCCL is loaded
+// with dlopen("libnccl.so.2") on first use so that libsb_cuda.so itself does not depend on it (inside a
+// PyTorch process this resolves to the NCCL build torch already loaded).  bench.py exercises the same
+// recipe with one process per GPU through torch.distributed (sycl-bench_b200/sharded.py).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <new>
+#include <vector>
+
+#include "sb_common.cuh"
+
+namespace {
+
+struct NcclApi {
+  void* handle = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  bool ok = false;
+};
+
+NcclApi& nccl() {
+  static NcclApi api = [] {
+    NcclApi a;
+    a.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if(!a.handle) a.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if(!a.handle) return a;
+    a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(a.handle, "ncclCommInitAll"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.handle, "ncclCommDestroy"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(a.handle, "ncclAllReduce"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(a.handle, "ncclAllGather"));
+    a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(a.handle, "ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(a.handle, "ncclGroupEnd"));
+    a.ok = a.CommInitAll && a.CommDestroy && a.AllReduce && a.AllGather && a.GroupStart && a.GroupEnd;
+    return a;
+  }();
+  return api;
+}
+
+size_t dtype_size(int dtype) {
+  switch(dtype) {
+  case SB_I32: case SB_F32: return 4;
+  case SB_I64: case SB_F64: return 8;
+  default: return 0;
+  }
+}
+
+ncclDataType_t nccl_type(int dtype) {
+  switch(dtype) {
+  case SB_I32: return ncclInt32;
+  case SB_I64: return ncclInt64;
+  case SB_F32: return ncclFloat32;
+  default: return ncclFloat64;
+  }
+}
+
+int reduce_call(sb_ctx* c, int dtype, const void* in, size_t n, void* out) {
+  switch(dtype) {
+  case SB_I32: return sb_reduce_i32(c, (const int32_t*)in, n, (int32_t*)out);
+  case SB_I64: return sb_reduce_i64(c, (const int64_t*)in, n, (int64_t*)out);
+  case SB_F32: return sb_reduce_f32(c, (const float*)in, n, (float*)out);
+  default: return sb_reduce_f64(c, (const double*)in, n, (double*)out);
+  }
+}
+int scan_call(sb_ctx* c, int dtype, const void* in, void* out, size_t n, int exclusive, const void* seed) {
+  switch(dtype) {
+  case SB_I32: return sb_scan_i32(c, (const int32_t*)in, (int32_t*)out, n, exclusive, 0, (const int32_t*)seed);
+  case SB_I64: return sb_scan_i64(c, (const int64_t*)in, (int64_t*)out, n, exclusive, 0, (const int64_t*)seed);
+  case SB_F32: return sb_scan_f32(c, (const float*)in, (float*)out, n, exclusive, 0, (const float*)seed);
+  default: return sb_scan_f64(c, (const double*)in, (double*)out, n, exclusive, 0, (const double*)seed);
+  }
+}
+int excl_carry_call(sb_ctx* c, int dtype, const void* totals, int rank, void* carry) {
+  switch(dtype) {
+  case SB_I32: return sb_exclusive_carry_i32(c, (const int32_t*)totals, rank, (int32_t*)carry);
+  case SB_I64: return sb_exclusive_carry_i64(c, (const int64_t*)totals, rank, (int64_t*)carry);
+  case SB_F32: return sb_exclusive_carry_f32(c, (const float*)totals, rank, (float*)carry);
+  default: return sb_exclusive_carry_f64(c, (const double*)totals, rank, (double*)carry);
+  }
+}
+int carry_add_call(sb_ctx* c, int dtype, void* buf, size_t n, const void* carry) {
+  switch(dtype) {
+  case SB_I32: return sb_carry_add_i32(c, (int32_t*)buf, n, (const int32_t*)carry);
+  case SB_I64: return sb_carry_add_i64(c, (int64_t*)buf, n, (const int64_t*)carry);
+  case SB_F32: return sb_carry_add_f32(c, (float*)buf, n, (const float*)carry);
+  default: return sb_carry_add_f64(c, (double*)buf, n, (const double*)carry);
+  }
+}
+
+}  // namespace
+
+struct sb_comm {
+  int n = 0;
+  std::vector<sb_ctx*> ctx;       // ctx[0] is borrowed, the others are owned
+  std::vector<ncclComm_t> comms;
+  std::vector<void*> scratch;     // per rank: [0, 8) carry, [64, 64 + 8 n) gathered totals
+  std::vector<cudaEvent_t> done;  // per rank: end of its part of an operation
+  cudaEvent_t start = nullptr;    // on rank 0: everything enqueued before the operation
+};
+
+namespace {
+// Ranks 1.. start after whatever rank 0's stream already holds, so that events recorded on rank 0's stream
+// (sb_timer_begin / sb_timer_end) bracket the whole sharded operation.
+int comm_fork(sb_comm* c) {
+  if(c->n == 1) return SB_OK;
+  {
+    sb_device_guard guard(c->ctx[0]->device);
+    SB_CUDA_TRY(cudaEventRecord(c->start, c->ctx[0]->stream));
+  }
+  for(int r = 1; r < c->n; ++r) {
+    sb_device_guard guard(c->ctx[r]->device);
+    SB_CUDA_TRY(cudaStreamWaitEvent(c->ctx[r]->stream, c->start, 0));
+  }
+  return SB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int sb_comm_create(sb_ctx* rank0, int ngpus, sb_comm** out) {
+  if(!rank0 || !out || ngpus < 1) return SB_ERR_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if(cudaGetDeviceCount(&ndev) != cudaSuccess || rank0->device + ngpus > ndev) return SB_ERR_NO_DEVICE;
+  if(ngpus > 1 && !nccl().ok) return SB_ERR_NCCL;
+  sb_comm* c = new(std::nothrow) sb_comm();
+  if(!c) return SB_ERR_WORKSPACE;
+  c->n = ngpus;
+  c->ctx.assign(ngpus, nullptr);
+  c->comms.assign(ngpus, nullptr);
+  c->scratch.assign(ngpus, nullptr);
+  c->done.assign(ngpus, nullptr);
+  c->ctx[0] = rank0;
+  int rc = SB_OK;
+  for(int r = 1; r < ngpus && rc == SB_OK; ++r) rc = sb_ctx_create(rank0->device + r, SB_STREAM_OWNED, &c->ctx[r]);
+  for(int r = 0; r < ngpus && rc == SB_OK; ++r) {
+    sb_device_guard guard(c->ctx[r]->device);
+    if(cudaMalloc(&c->scratch[r], 64 + 8 * (size_t)ngpus) != cudaSuccess) rc = SB_ERR_WORKSPACE;
+    else if(cudaEventCreateWithFlags(&c->done[r], cudaEventDisableTiming) != cudaSuccess) rc = SB_ERR_WORKSPACE;
+  }
+  if(rc == SB_OK) {
+    sb_device_guard guard(rank0->device);
+    if(cudaEventCreateWithFlags(&c->start, cudaEventDisableTiming) != cudaSuccess) rc = SB_ERR_WORKSPACE;
+  }
+  if(rc == SB_OK && ngpus > 1) {
+    std::vector<int> devs(ngpus);
+    for(int r = 0; r < ngpus; ++r) devs[r] = c->ctx[r]->device;
+    if(nccl().CommInitAll(c->comms.data(), ngpus, devs.data()) != ncclSuccess) rc = SB_ERR_NCCL;
+  }
+  if(rc != SB_OK) {
+    sb_comm_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return SB_OK;
+}
+
+int sb_comm_destroy(sb_comm* c) {
+  if(!c) return SB_OK;
+  for(int r = 0; r < c->n; ++r) {
+    if(!c->ctx[r]) continue;
+    sb_device_guard guard(c->ctx[r]->device);
+    cudaStreamSynchronize(c->ctx[r]->stream);
+    if(c->comms[r]) nccl().CommDestroy(c->comms[r]);
+    if(c->scratch[r]) cudaFree(c->scratch[r]);
+    if(c->done[r]) cudaEventDestroy(c->done[r]);
+    if(r > 0) sb_ctx_destroy(c->ctx[r]);
+  }
+  if(c->start) cudaEventDestroy(c->start);
+  (void)cudaGetLastError();
+  delete c;
+  return SB_OK;
+}
+
+int sb_comm_size(sb_comm* c) { return c ? c->n : 0; }
+sb_ctx* sb_comm_ctx(sb_comm* c, int rank) { return (c && rank >= 0 && rank < c->n) ? c->ctx[rank] : nullptr; }
+
+int sb_comm_join(sb_comm* c) {
+  if(!c) return SB_ERR_BAD_ARG;
+  for(int r = 1; r < c->n; ++r) {
+    {
+      sb_device_guard guard(c->ctx[r]->device);
+      SB_CUDA_TRY(cudaEventRecord(c->done[r], c->ctx[r]->stream));
+    }
+    sb_device_guard guard(c->ctx[0]->device);
+    SB_CUDA_TRY(cudaStreamWaitEvent(c->ctx[0]->stream, c->done[r], 0));
+  }
+  return SB_OK;
+}
+
+int sb_comm_reduce(sb_comm* c, int dtype, const void* const* in, const size_t* n, void* const* out) {
+  if(!c || !in || !n || !out || dtype_size(dtype) == 0) return SB_ERR_BAD_ARG;
+  if(int rc = comm_fork(c); rc != SB_OK) return rc;
+  for(int r = 0; r < c->n; ++r) {
+    int rc = reduce_call(c->ctx[r], dtype, in[r], n[r], out[r]);
+    if(rc != SB_OK) return rc;
+  }
+  if(c->n > 1) {
+    if(nccl().GroupStart() != ncclSuccess) return SB_ERR_NCCL;
+    for(int r = 0; r < c->n; ++r)
+      if(nccl().AllReduce(out[r], out[r], 1, nccl_type(dtype), ncclSum, c->comms[r], c->ctx[r]->stream) != ncclSuccess) return SB_ERR_NCCL;
+    if(nccl().GroupEnd() != ncclSuccess) return SB_ERR_NCCL;
+  }
+  return sb_comm_join(c);
+}
+
+int sb_comm_scan(sb_comm* c, int dtype, const void* const* in, void* const* out, const size_t* n, int exclusive, int strategy) {
+  const size_t s = dtype_size(dtype);
+  if(!c || !in || !n || !out || s == 0) return SB_ERR_BAD_ARG;
+  if(strategy == SB_SCAN_THEN_CARRY && exclusive) return SB_ERR_BAD_ARG;
+  if(c->n == 1) {
+    int rc = scan_call(c->ctx[0], dtype, in[0], out[0], n[0], exclusive, nullptr);
+    return rc;
+  }
+  if(int rc = comm_fork(c); rc != SB_OK) return rc;
+  auto carry = [&](int r) { return c->scratch[r]; };
+  auto totals = [&](int r) { return (void*)((char*)c->scratch[r] + 64); };
+  // 1. shard totals
+  for(int r = 0; r < c->n; ++r) {
+    int rc;
+    if(strategy == SB_REDUCE_THEN_SCAN) {
+      rc = reduce_call(c->ctx[r], dtype, in[r], n[r], carry(r));
+    } else {
+      rc = scan_call(c->ctx[r], dtype, in[r], out[r], n[r], 0, nullptr);
+      if(rc == SB_OK) {
+        sb_device_guard guard(c->ctx[r]->device);
+        if(n[r]) SB_CUDA_TRY(cudaMemcpyAsync(carry(r), (const char*)out[r] + (n[r] - 1) * s, s, cudaMemcpyDeviceToDevice, c->ctx[r]->stream));
+        else SB_CUDA_TRY(cudaMemsetAsync(carry(r), 0, s, c->ctx[r]->stream));
+      }
+    }
+    if(rc != SB_OK) return rc;
+  }
+  // 2. one element per rank crosses NVLink
+  if(nccl().GroupStart() != ncclSuccess) return SB_ERR_NCCL;
+  for(int r = 0; r < c->n; ++r)
+    if(nccl().AllGather(carry(r), totals(r), 1, nccl_type(dtype), c->comms[r], c->ctx[r]->stream) != ncclSuccess) return SB_ERR_NCCL;
+  if(nccl().GroupEnd() != ncclSuccess) return SB_ERR_NCCL;
+  // 3. exclusive carry on the device, then the seeded scan / the carry-add pass
+  for(int r = 0; r < c->n; ++r) {
+    int rc = excl_carry_call(c->ctx[r], dtype, totals(r), r, carry(r));
+    if(rc != SB_OK) return rc;
+    if(strategy == SB_REDUCE_THEN_SCAN) rc = scan_call(c->ctx[r], dtype, in[r], out[r], n[r], exclusive, carry(r));
+    else rc = carry_add_call(c->ctx[r], dtype, out[r], n[r], carry(r));
+    if(rc != SB_OK) return rc;
+  }
+  return sb_comm_join(c);
+}
+
+}  // extern "C"

@@ -20,6 +20,7 @@ const char* sb_strerror(int status) {
   case SB_ERR_NO_DEVICE: return "sb: no CUDA device (libsb_cuda has no CPU fallback)";
   case SB_ERR_UNSUPPORTED: return "sb: device is not compute capability 10.x (library is sm_100a only)";
   case SB_ERR_TIMER: return "sb: sb_timer_end without sb_timer_begin";
+  case SB_ERR_NCCL: return "sb: NCCL unavailable (libnccl.so.2 not loadable) or an NCCL call failed";
   default: break;
   }
   if(status > 0) return cudaGetErrorString((cudaError_t)status);

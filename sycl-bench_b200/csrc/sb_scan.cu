@@ -42,6 +42,8 @@
 //  carries a per-launch epoch, so descriptors are never reset between launches.  Segmented
 //  variants run the same code on (value, head-flag) pairs: (v1,f1)(+)(v2,f2) = (f2 ? v2 : v1+v2,
 //  f1|f2); if every tile starts on a head (power-of-two segment <= tile) no descriptor is touched.
+#include <atomic>
+
 #include "sb_common.cuh"
 
 namespace {
@@ -913,12 +915,23 @@ scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg
   }
 }
 
-// co-resident CTAs per SM of a persistent kernel instantiation (queried once per process)
+// co-resident CTAs per SM of a persistent kernel instantiation.  The shared-memory opt-in is a per-device
+// function attribute, so the query (and the opt-in) is made once per device, on the current device.
+constexpr int SB_MAX_DEVICES = 64;
+struct OccupancyCache {
+  std::atomic<int> per_sm[SB_MAX_DEVICES];  // 0: not queried yet, -1: does not fit
+};
 template <typename Kern>
-int resident_ctas_per_sm(Kern kern, int threads, size_t smem) {
-  int nb = 0;
-  if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess) return 0;
+int resident_ctas_per_sm(OccupancyCache& cache, int device, Kern kern, int threads, size_t smem) {
+  if(device < 0 || device >= SB_MAX_DEVICES) return 0;
+  int nb = cache.per_sm[device].load(std::memory_order_acquire);
+  if(nb != 0) return nb;
+  if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess || nb <= 0) {
+    (void)cudaGetLastError();
+    nb = -1;
+  }
+  cache.per_sm[device].store(nb, std::memory_order_release);
   return nb;
 }
 
@@ -930,14 +943,15 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
     const A* seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, size_t tiles) {
   constexpr int K = ws_rows<MODE>::K;
   constexpr size_t smem = (size_t)WS_STAGES * ws_stage_bytes<A, MODE, K>();
-  static const int per_sm = resident_ctas_per_sm(scan_ws_kernel<A, MODE, K>, WS_THREADS, smem);
+  static OccupancyCache ws_cache, ind_cache;
+  const int per_sm = resident_ctas_per_sm(ws_cache, ctx->device, scan_ws_kernel<A, MODE, K>, WS_THREADS, smem);
   if(per_sm <= 0) return SB_ERR_WORKSPACE;
   size_t grid = (size_t)ctx->sm_count * per_sm;
   if(grid > tiles) grid = tiles;
   int flags_in_ring = (MODE == MODE_FLAGS && sb::aligned_to(flags, 16)) ? 1 : 0;  // TMA needs 16-byte aligned sources
   long long num_tiles = (long long)tiles;
   if(!use_lookback) {
-    static const int ind_per_sm = resident_ctas_per_sm(scan_independent_kernel<A, MODE, K>, (WS_NW + 1) * 32, smem);
+    const int ind_per_sm = resident_ctas_per_sm(ind_cache, ctx->device, scan_independent_kernel<A, MODE, K>, (WS_NW + 1) * 32, smem);
     if(ind_per_sm <= 0) return SB_ERR_WORKSPACE;
     size_t g = (size_t)ctx->sm_count * ind_per_sm;
     if(g > tiles) g = tiles;

@@ -87,15 +87,17 @@ inline bool value_matches(T got, uint64_t exact_mod64, long double exact_real, s
 // ---- scan-family verification -------------------------------------------------------------------------------
 // integers: every element on the device against the closed form (sb_check_iota); floating point: the
 // first and last 2^16 elements plus 2^16 strided samples against the closed form within the tolerance.
+// `out` holds elements [offset, offset + n) of a scan over `total` elements (offset = 0, total = n unless sharded).
 template <class T>
-bool verify_scan(sb_ctx* ctx, const PrefetchedBuffer<T>& out, size_t n, bool exclusive, size_t L) {
+bool verify_scan(sb_ctx* ctx, const PrefetchedBuffer<T>& out, size_t n, bool exclusive, size_t L, size_t offset = 0, size_t total = 0) {
   if(n == 0) return true;
+  if(total == 0) total = n;
   if constexpr(std::is_same_v<T, int> || std::is_same_v<T, long long>) {
     PrefetchedBuffer<unsigned long long> bad;
     bad.initialize(ctx, 1);
     int rc;
-    if constexpr(std::is_same_v<T, int>) rc = sb_check_iota_i32(ctx, reinterpret_cast<const int32_t*>(out.get()), n, 0, exclusive ? 1 : 0, L, reinterpret_cast<uint64_t*>(bad.get()));
-    else rc = sb_check_iota_i64(ctx, reinterpret_cast<const int64_t*>(out.get()), n, 0, exclusive ? 1 : 0, L, reinterpret_cast<uint64_t*>(bad.get()));
+    if constexpr(std::is_same_v<T, int>) rc = sb_check_iota_i32(ctx, reinterpret_cast<const int32_t*>(out.get()), n, offset, exclusive ? 1 : 0, L, reinterpret_cast<uint64_t*>(bad.get()));
+    else rc = sb_check_iota_i64(ctx, reinterpret_cast<const int64_t*>(out.get()), n, offset, exclusive ? 1 : 0, L, reinterpret_cast<uint64_t*>(bad.get()));
     sb::check(rc, "sb_check_iota");
     return bad.get_host_access()[0] == 0;
   } else {
@@ -103,7 +105,7 @@ bool verify_scan(sb_ctx* ctx, const PrefetchedBuffer<T>& out, size_t n, bool exc
     auto check_window = [&](size_t begin, size_t count) {
       const auto h = out.get_host_access(begin, count);
       for(size_t i = 0; i < count; ++i)
-        if(!value_matches<T>(h[i], 0, scan_value_ld(begin + i, exclusive, L), n)) return false;
+        if(!value_matches<T>(h[i], 0, scan_value_ld(offset + begin + i, exclusive, L), total)) return false;
       return true;
     };
     if(!check_window(0, win) || !check_window(n - win, win)) return false;

@@ -15,5 +15,6 @@ int main(int argc, char** argv) {
   } else {
     std::cerr << "prefixsum: --no-ndrange-kernels leaves nothing to run (see DESIGN.md)\n";
   }
+  pattern::release_comms();
   return app.exitCode();
 }

@@ -11,7 +11,9 @@
 //  * verify() checks the value against the closed form (integers bit-exact, floating point within
 //    1e-5*log2 N / 1e-12*log2 N relative).  Upstream's own check (:59-68) accumulates in `int`
 //    and prints FAIL for every N > 65 536; `--reference-verify` reproduces that verdict verbatim.
-#include "pattern_common.h"
+//  * --num-gpus=N (no upstream counterpart): N contiguous shards on N devices, sb_comm_reduce =
+//    one sb_reduce per shard + one NCCL all-reduce of a single element (pattern/sharded.h).
+#include "sharded.h"
 
 template <typename T>
 class Reduction {
@@ -20,6 +22,9 @@ protected:
   PrefetchedBuffer<T> _input_buff;
   PrefetchedBuffer<T> _output_buff;
   std::size_t _n = 0;  // elements actually reduced
+  int _gpus = 1;
+  sb_comm* _comm = nullptr;
+  pattern::ShardedArray<T> _shards, _results;
 
 public:
   Reduction(const BenchmarkArgs& args) : _args{args} {}
@@ -27,6 +32,14 @@ public:
   void setup() {
     const std::size_t L = std::max<std::size_t>(_args.local_size, 1);
     _n = (_args.problem_size / L) * L;
+    _gpus = pattern::requested_gpus(_args);
+    if(_gpus > 1) {
+      _comm = pattern::comm_for(_args, _gpus);
+      _shards.initialize(_comm, _n);
+      _shards.fill_iota();
+      _results.initialize_scalars(_comm);
+      return;
+    }
     if(_args.cli.isFlagSet("--host-input")) {
       // generate_input() on the host and upload, like upstream setup() (:31-42)
       std::vector<T> host(_args.problem_size);
@@ -40,12 +53,22 @@ public:
   }
 
   void run(std::vector<sb::event>& events) {
+    if(_gpus > 1) {
+      sb::check(sb_comm_reduce(_comm, pattern::DtypeOf<T>::value, _shards.in_ptrs(), _shards.counts(), _results.out_ptrs()), "sb_comm_reduce");
+      events.push_back({"sb_comm_reduce"});
+      return;
+    }
     sb::check(pattern::Ops<T>::reduce(_args.ctx(), _input_buff.get(), _n, _output_buff.get()), "sb_reduce");
     events.push_back({"sb_reduce"});
   }
 
   bool verify(VerificationSetting&) {
-    const T result = _output_buff.get_host_access()[0];
+    const T result = _gpus > 1 ? _results.shard(0).get_host_access()[0] : _output_buff.get_host_access()[0];
+    if constexpr(std::is_integral_v<T>) {
+      // every rank holds the same total after the all-reduce
+      for(int r = 1; r < _gpus; ++r)
+        if(_results.shard(r).get_host_access()[0] != result) return false;
+    }
     if(_args.cli.isFlagSet("--reference-verify")) return reference_verify(result);
     const uint64_t exact = _n == 0 ? 0 : pattern::tri(_n - 1);
     const long double real = _n == 0 ? 0.0L : pattern::tri_ld((long double)(_n - 1));
@@ -90,5 +113,6 @@ int main(int argc, char** argv) {
   } else {
     std::cerr << "reduction: --no-ndrange-kernels leaves nothing to run (one CUDA kernel backs the NDRange rows; see DESIGN.md)\n";
   }
+  pattern::release_comms();
   return app.exitCode();
 }

@@ -2,7 +2,7 @@
 // stubs (/root/reference/pattern/prefixsum.cpp:1, scan.cpp:1, segmentedscan.cpp:1), so the
 // semantics are the written contract of DESIGN.md §Scan semantics.
 #pragma once
-#include "pattern_common.h"
+#include "sharded.h"
 
 namespace pattern {
 
@@ -14,6 +14,10 @@ protected:
   BenchmarkArgs _args;
   PrefetchedBuffer<T> _in, _out;
   PrefetchedBuffer<uint8_t> _flags;
+  // --num-gpus=N (PrefixSum only): contiguous shards, sb_comm_scan
+  int _gpus = 1;
+  sb_comm* _comm = nullptr;
+  ShardedArray<T> _in_shards, _out_shards;
 
   static constexpr bool exclusive() { return KIND == ScanKind::ScanGlobal || KIND == ScanKind::ScanGroup; }
   std::size_t restart() const { return (KIND == ScanKind::PrefixSum || KIND == ScanKind::ScanGlobal) ? 0 : _args.local_size; }
@@ -25,6 +29,15 @@ public:
     const std::size_t n = _args.problem_size;
     if(KIND != ScanKind::PrefixSum && KIND != ScanKind::ScanGlobal && _args.local_size == 0)
       throw std::invalid_argument("--local must be positive");
+    _gpus = requested_gpus(_args);
+    if(_gpus > 1) {
+      if(KIND != ScanKind::PrefixSum) throw std::invalid_argument("--num-gpus is implemented for reduction and prefixsum");
+      _comm = comm_for(_args, _gpus);
+      _in_shards.initialize(_comm, n);
+      _out_shards.initialize(_comm, n);
+      _in_shards.fill_iota();
+      return;
+    }
     _in.initialize(_args.ctx(), n);
     _out.initialize(_args.ctx(), n);
     sb::check(Ops<T>::iota(_args.ctx(), _in.get(), n, 0), "sb_iota");
@@ -38,6 +51,12 @@ public:
   void run(std::vector<sb::event>& events) {
     const std::size_t n = _args.problem_size;
     int rc;
+    if(_gpus > 1) {
+      const int strategy = _args.cli.getOrDefault<std::string>("--scan-strategy", "reduce_then_scan") == "scan_then_carry" ? SB_SCAN_THEN_CARRY : SB_REDUCE_THEN_SCAN;
+      sb::check(sb_comm_scan(_comm, DtypeOf<T>::value, _in_shards.in_ptrs(), _out_shards.out_ptrs(), _in_shards.counts(), 0, strategy), "sb_comm_scan");
+      events.push_back({"sb_comm_scan"});
+      return;
+    }
     if(KIND == ScanKind::PrefixSum) rc = Ops<T>::scan(_args.ctx(), _in.get(), _out.get(), n, 0, 0);
     else if(KIND == ScanKind::ScanGlobal) rc = Ops<T>::scan(_args.ctx(), _in.get(), _out.get(), n, 1, 0);
     else if(KIND == ScanKind::ScanGroup) rc = Ops<T>::scan(_args.ctx(), _in.get(), _out.get(), n, 1, _args.local_size);
@@ -47,7 +66,14 @@ public:
     events.push_back({"sb_scan"});
   }
 
-  bool verify(VerificationSetting&) { return verify_scan<T>(_args.ctx(), _out, _args.problem_size, exclusive(), restart()); }
+  bool verify(VerificationSetting&) {
+    if(_gpus > 1) {
+      for(int r = 0; r < _gpus; ++r)
+        if(!verify_scan<T>(sb_comm_ctx(_comm, r), _out_shards.shard(r), _out_shards.count(r), exclusive(), restart(), _out_shards.begin(r), _args.problem_size)) return false;
+      return true;
+    }
+    return verify_scan<T>(_args.ctx(), _out, _args.problem_size, exclusive(), restart());
+  }
 
   static ThroughputMetric getThroughputMetric(const BenchmarkArgs& args) {
     const double n = static_cast<double>(args.problem_size);

@@ -97,6 +97,14 @@ def lib() -> C.CDLL:
     L.sb_host_scan.argtypes = [vp, i, vp, vp, sz, i, sz]
     L.sb_host_segreduce.argtypes = [vp, i, vp, sz, sz]
     L.sb_host_segscan.argtypes = [vp, i, vp, vp, sz, sz, vp, i]
+    L.sb_comm_create.argtypes = [vp, i, C.POINTER(vp)]
+    L.sb_comm_destroy.argtypes = [vp]
+    L.sb_comm_size.argtypes = [vp]
+    L.sb_comm_ctx.argtypes = [vp, i]
+    L.sb_comm_ctx.restype = vp
+    L.sb_comm_join.argtypes = [vp]
+    L.sb_comm_reduce.argtypes = [vp, i, C.POINTER(vp), C.POINTER(sz), C.POINTER(vp)]
+    L.sb_comm_scan.argtypes = [vp, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz), i, i]
     _lib = L
     return L
 
@@ -258,6 +266,74 @@ class Context:
         n = _numel(h_in) if n is None else n
         _check(lib().sb_host_segscan(self._h, _DTYPE_ENUM[t], _ptr(h_in), _ptr(h_out), n, seg_len, _ptr(head_flags), int(exclusive)))
         return h_out
+
+
+class _BorrowedContext(Context):
+    """A Context whose handle belongs to an sb_comm."""
+
+    def close(self) -> None:
+        self._h = C.c_void_p()
+
+
+class Comm:
+    """Single-process multi-GPU group (sb_comm_* in include/sb_cuda.h): rank r works on device
+    ctx.device + r with its own stream; one NCCL collective of one element per rank joins the shards.
+    bench.py uses the one-process-per-GPU form of the same recipe (sharded.ShardedOps) instead."""
+
+    REDUCE_THEN_SCAN = 0
+    SCAN_THEN_CARRY = 1
+
+    def __init__(self, ctx: Context, ngpus: int):
+        self._h = C.c_void_p()
+        self._root = ctx  # keeps rank 0 alive
+        _check(lib().sb_comm_create(ctx._h, ngpus, C.byref(self._h)))
+        self.size = ngpus
+
+    def close(self) -> None:
+        if self._h:
+            lib().sb_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def rank_ctx(self, rank: int) -> Context:
+        """A borrowed Context view of rank `rank` (do not close it)."""
+        h = lib().sb_comm_ctx(self._h, rank)
+        if not h:
+            raise IndexError(rank)
+        view = _BorrowedContext.__new__(_BorrowedContext)
+        view._h = C.c_void_p(h)
+        view.device = self._root.device + rank
+        return view
+
+    def join(self) -> None:
+        _check(lib().sb_comm_join(self._h))
+
+    @staticmethod
+    def _arr(ctype, values):
+        return (ctype * len(values))(*values)
+
+    def reduce(self, shards, outs, dtype: Optional[str] = None):
+        """shards[r] / outs[r] live on device r; every outs[r][0] receives the global sum."""
+        t = dtype or dtype_of(shards[0])
+        ins = self._arr(C.c_void_p, [_ptr(x) for x in shards])
+        ns = self._arr(C.c_size_t, [_numel(x) for x in shards])
+        os_ = self._arr(C.c_void_p, [_ptr(x) for x in outs])
+        _check(lib().sb_comm_reduce(self._h, _DTYPE_ENUM[t], ins, ns, os_))
+        return outs
+
+    def scan(self, shards, outs, exclusive: bool = False, strategy: int = 0, dtype: Optional[str] = None):
+        """Global prefix sum over the concatenation of the shards (rank order)."""
+        t = dtype or dtype_of(shards[0])
+        ins = self._arr(C.c_void_p, [_ptr(x) for x in shards])
+        ns = self._arr(C.c_size_t, [_numel(x) for x in shards])
+        os_ = self._arr(C.c_void_p, [_ptr(x) for x in outs])
+        _check(lib().sb_comm_scan(self._h, _DTYPE_ENUM[t], ins, os_, ns, int(exclusive), strategy))
+        return outs
 
 
 def _numel(x) -> int:
