@@ -110,6 +110,14 @@ int sb_iota_i64(sb_ctx*, int64_t* out, size_t n, uint64_t offset);
 int sb_iota_f32(sb_ctx*, float* out, size_t n, uint64_t offset);
 int sb_iota_f64(sb_ctx*, double* out, size_t n, uint64_t offset);
 
+/* out[i] = value: the device-side form of `std::fill(in_vec.begin(), in_vec.end(), 1)` + upload in the
+ * sycl2020 reduction trio (sycl2020/atomics/atomic_reduction.cpp:19-27,
+ * sycl2020/group_algorithms/reduce_over_group.cpp:21-29, sycl2020/kernel_reduction/kernel_reduction.cpp:19-27). */
+int sb_fill_i32(sb_ctx*, int32_t* out, size_t n, int32_t value);
+int sb_fill_i64(sb_ctx*, int64_t* out, size_t n, int64_t value);
+int sb_fill_f32(sb_ctx*, float* out, size_t n, float value);
+int sb_fill_f64(sb_ctx*, double* out, size_t n, double value);
+
 /* ---- reduction ------------------------------------------------------------------------------ */
 /* out[0] = sum(in[0..n)), one launch.  Replaces the whole multi-pass driver
  * Reduction<T>::submit (pattern/reduction.cpp:71-97) and both kernels

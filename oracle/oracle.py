@@ -52,6 +52,18 @@ def lib() -> C.CDLL:
             getattr(L, f"cpu_sum_{t}").argtypes = [vp, sz]
             getattr(L, f"cpu_sum_{t}").restype = CT[t]
             getattr(L, f"cpu_scan_{t}").argtypes = [vp, vp, sz, i]
+        # sycl2020 reduction trio (oracle/sb_oracle_sycl2020.c)
+        L.ref2020_percent_diff.argtypes = [C.c_double, C.c_double]
+        L.ref2020_percent_diff.restype = C.c_float
+        for t in REF_REDUCTION_TYPES:
+            getattr(L, f"ref2020_atomic_{t}").argtypes = [u64]
+            getattr(L, f"ref2020_atomic_{t}").restype = CT[t]
+            getattr(L, f"ref2020_group_{t}").argtypes = [u64, u64]
+            getattr(L, f"ref2020_group_{t}").restype = CT[t]
+            getattr(L, f"ref2020_kernel_{t}").argtypes = [u64, u64]
+            getattr(L, f"ref2020_kernel_{t}").restype = CT[t]
+            getattr(L, f"ref2020_verify_atomic_{t}").argtypes = [CT[t], u64]
+            getattr(L, f"ref2020_verify_size_{t}").argtypes = [CT[t], u64]
         L.kat_reduce.argtypes = [u64]
         L.kat_reduce.restype = u64
         L.kat_scan.argtypes = [u64, i, u64]

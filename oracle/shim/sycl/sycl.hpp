@@ -1,6 +1,7 @@
 // Host-only stand-in for <sycl/sycl.hpp>, just large enough to compile the UNMODIFIED reference
-// translation units /root/reference/pattern/{reduction,segmentedreduction}.cpp (and the harness
-// headers they include) with plain g++.  No SYCL implementation exists in this image
+// translation units /root/reference/pattern/{reduction,segmentedreduction}.cpp, the reduction trio
+// /root/reference/sycl2020/{atomics/atomic_reduction,group_algorithms/reduce_over_group,
+// kernel_reduction/kernel_reduction}.cpp (and the harness headers they include) with plain g++.  No SYCL implementation exists in this image
 // (SURVEY.md F5), so this is how the reference's own arithmetic is executed for the oracle and for
 // the CPU baseline ("reference source on an in-repo host shim").
 //
@@ -282,6 +283,7 @@ public:
     detail::dump_host_access(impl->storage.data(), impl->count * sizeof(T));
     return host_accessor<T, D>(impl->storage.data(), impl->count);
   }
+  T* device_data() const { return impl->storage.data(); } // shim-internal (sycl::reduction)
 
 private:
   std::shared_ptr<detail::buffer_impl<T>> impl;
@@ -353,6 +355,7 @@ struct fiber_group {
   std::vector<ucontext_t> ctx;
   std::vector<char> stacks;
   std::vector<char> done;
+  std::vector<char> collective; // one 16-byte slot per work-item + one for the result (group algorithms)
   std::size_t current = 0;
   std::function<void(std::size_t)> body;
 };
@@ -378,6 +381,7 @@ inline void run_group_with_fibers(fiber_group& fg, std::size_t lsize) {
   fg.ctx.resize(lsize);
   fg.stacks.resize(lsize * STACK);
   fg.done.assign(lsize, 0);
+  if(fg.collective.size() < (lsize + 1) * 16) fg.collective.resize((lsize + 1) * 16);
   for(std::size_t l = 0; l < lsize; ++l) {
     getcontext(&fg.ctx[l]);
     fg.ctx[l].uc_stack.ss_sp = fg.stacks.data() + l * STACK;
@@ -402,6 +406,83 @@ inline void run_group_with_fibers(fiber_group& fg, std::size_t lsize) {
 
 template <int D>
 inline void group_barrier(const group<D>&) { detail::fiber_barrier(); }
+
+// ---- SYCL 2020 pieces used by sycl2020/{atomics,group_algorithms,kernel_reduction} ------------------------------
+template <typename T = void>
+struct plus {
+  T operator()(const T& a, const T& b) const { return a + b; }
+};
+
+enum class memory_order { relaxed, acquire, release, acq_rel, seq_cst };
+enum class memory_scope { work_item, sub_group, work_group, device, system };
+namespace access {
+enum class address_space { global_space, local_space, constant_space, private_space, generic_space };
+}
+
+// fetch_add only: integers through the GCC atomic builtins, floating point through a CAS loop on the bits
+template <typename T, memory_order O, memory_scope S, access::address_space A = access::address_space::generic_space>
+class atomic_ref {
+public:
+  explicit atomic_ref(T& r) : p(&r) {}
+  T fetch_add(T v) const {
+    if constexpr(std::is_integral_v<T>) {
+      return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+    } else {
+      using U = std::conditional_t<sizeof(T) == 4, std::uint32_t, std::uint64_t>;
+      U* up = reinterpret_cast<U*>(p);
+      U old = __atomic_load_n(up, __ATOMIC_RELAXED);
+      for(;;) {
+        T cur;
+        std::memcpy(&cur, &old, sizeof(T));
+        const T next = cur + v;
+        U bits;
+        std::memcpy(&bits, &next, sizeof(T));
+        if(__atomic_compare_exchange_n(up, &old, bits, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return cur;
+      }
+    }
+  }
+
+private:
+  T* p;
+};
+
+// reduce_over_group inside an nd_range kernel: every work-item parks its value, work-item 0 folds them in
+// local-id order, everybody reads the total (two fiber barriers)
+template <int D, typename T, typename Op>
+inline T reduce_over_group(const group<D>&, T x, Op op) {
+  static_assert(sizeof(T) <= 16, "collective slot too small");
+  detail::fiber_group* fg = detail::tls_fibers;
+  if(!fg) return x;
+  const std::size_t L = fg->ctx.size(), me = fg->current;
+  auto slot = [&](std::size_t i) { return reinterpret_cast<T*>(fg->collective.data() + i * 16); };
+  *slot(me) = x;
+  detail::fiber_barrier();
+  if(me == 0) {
+    T acc = *slot(0);
+    for(std::size_t l = 1; l < L; ++l) acc = op(acc, *slot(l));
+    *slot(L) = acc;
+  }
+  detail::fiber_barrier();
+  return *slot(L);
+}
+
+namespace detail {
+template <typename T, typename Op>
+struct reduction_desc {
+  T* target; // combined with the value already stored there (no initialize_to_identity property)
+  Op op;
+};
+template <typename T, typename Op>
+struct reducer {
+  T value;
+  Op op;
+  void combine(const T& v) { value = op(value, v); }
+  reducer& operator+=(const T& v) {
+    combine(v);
+    return *this;
+  }
+};
+} // namespace detail
 
 // ---- handler ----------------------------------------------------------------------------------------------------------------
 class handler {
@@ -432,6 +513,31 @@ public:
     }
   }
 
+  // parallel_for(range, reduction, f(id, reducer&)): one private reducer per OpenMP thread over a static
+  // schedule, partials folded in thread order (the combination order is implementation-defined in SYCL)
+  template <typename Name = void, typename T, typename Op, typename F>
+  void parallel_for(range<1> r, detail::reduction_desc<T, Op> red, F f) {
+    const std::size_t n = r[0];
+    std::vector<T> partial;
+#pragma omp parallel
+    {
+#ifdef _OPENMP
+      const int tid = omp_get_thread_num(), nth = omp_get_num_threads();
+#else
+      const int tid = 0, nth = 1;
+#endif
+#pragma omp single
+      partial.assign(nth, T(0));
+      detail::reducer<T, Op> rd{T(0), red.op};
+#pragma omp for schedule(static)
+      for(std::size_t i = 0; i < n; ++i) f(id<1>(i), rd);
+      partial[tid] = rd.value;
+    }
+    T acc = *red.target;
+    for(const T& p : partial) acc = red.op(acc, p);
+    *red.target = acc;
+  }
+
   template <typename Name = void, typename F>
   void parallel_for(nd_range<1> ndr, F f) {
     const std::size_t L = ndr.get_local_range()[0];
@@ -451,6 +557,11 @@ public:
     }
   }
 };
+
+template <typename T, int D, typename Op>
+inline detail::reduction_desc<T, Op> reduction(buffer<T, D>& b, handler&, Op op) {
+  return detail::reduction_desc<T, Op>{b.device_data(), op};
+}
 
 template <typename T, int D>
 inline local_accessor<T, D>::local_accessor(range<D> r, handler& cgh) : offset(cgh.reserve_local(r.size() * sizeof(T))), count(r.size()) {}

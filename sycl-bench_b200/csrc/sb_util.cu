@@ -31,6 +31,24 @@ __global__ void __launch_bounds__(UT_NT) iota_kernel(A* __restrict__ out, size_t
 }
 
 template <typename A>
+__global__ void __launch_bounds__(UT_NT) fill_kernel(A* __restrict__ out, size_t n, A value, int aligned) {
+  constexpr int VEC = 16 / sizeof(A);
+  const size_t stride = (size_t)gridDim.x * UT_NT * VEC;
+  sb::Vec<A> v;
+#pragma unroll
+  for(int c = 0; c < VEC; ++c) v.v[c] = value;
+  for(size_t i = ((size_t)blockIdx.x * UT_NT + threadIdx.x) * VEC; i < n; i += stride) {
+    if(aligned && i + VEC <= n) {
+      sb::stg_vec<A>(out + i, v);
+    } else {
+#pragma unroll
+      for(int c = 0; c < VEC; ++c)
+        if(i + c < n) out[i + c] = value;
+    }
+  }
+}
+
+template <typename A>
 __global__ void __launch_bounds__(UT_NT) carry_add_kernel(A* __restrict__ buf, size_t n, const A* __restrict__ carry, int aligned) {
   constexpr int VEC = 16 / sizeof(A);
   constexpr int U = 4;
@@ -117,6 +135,20 @@ int iota_impl(sb_ctx* ctx, T* out, size_t n, uint64_t offset) {
 }
 
 template <typename T>
+int fill_impl(sb_ctx* ctx, T* out, size_t n, T value) {
+  using A = typename sb_arith<T>::type;
+  if(!ctx || (n && !out)) return SB_ERR_BAD_ARG;
+  if(!sb::aligned_to(out, sizeof(T))) return SB_ERR_MISALIGNED;
+  if(n == 0) return SB_OK;
+  sb_device_guard guard(ctx->device);
+  constexpr int VEC = 16 / sizeof(T);
+  const size_t blocks = grid_for(ctx, n, (size_t)UT_NT * VEC);
+  fill_kernel<A><<<(unsigned)blocks, UT_NT, 0, ctx->stream>>>(reinterpret_cast<A*>(out), n, (A)value, sb::aligned_to(out, 16) ? 1 : 0);
+  SB_CHECK_LAUNCH(ctx);
+  return SB_OK;
+}
+
+template <typename T>
 int carry_add_impl(sb_ctx* ctx, T* inout, size_t n, const T* carry) {
   using A = typename sb_arith<T>::type;
   if(!ctx || !carry || (n && !inout)) return SB_ERR_BAD_ARG;
@@ -164,6 +196,10 @@ int sb_iota_i32(sb_ctx* c, int32_t* o, size_t n, uint64_t off) { return iota_imp
 int sb_iota_i64(sb_ctx* c, int64_t* o, size_t n, uint64_t off) { return iota_impl<int64_t>(c, o, n, off); }
 int sb_iota_f32(sb_ctx* c, float* o, size_t n, uint64_t off) { return iota_impl<float>(c, o, n, off); }
 int sb_iota_f64(sb_ctx* c, double* o, size_t n, uint64_t off) { return iota_impl<double>(c, o, n, off); }
+int sb_fill_i32(sb_ctx* c, int32_t* o, size_t n, int32_t v) { return fill_impl<int32_t>(c, o, n, v); }
+int sb_fill_i64(sb_ctx* c, int64_t* o, size_t n, int64_t v) { return fill_impl<int64_t>(c, o, n, v); }
+int sb_fill_f32(sb_ctx* c, float* o, size_t n, float v) { return fill_impl<float>(c, o, n, v); }
+int sb_fill_f64(sb_ctx* c, double* o, size_t n, double v) { return fill_impl<double>(c, o, n, v); }
 
 int sb_carry_add_i32(sb_ctx* c, int32_t* p, size_t n, const int32_t* k) { return carry_add_impl<int32_t>(c, p, n, k); }
 int sb_carry_add_i64(sb_ctx* c, int64_t* p, size_t n, const int64_t* k) { return carry_add_impl<int64_t>(c, p, n, k); }

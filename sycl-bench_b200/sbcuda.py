@@ -93,6 +93,8 @@ def lib() -> C.CDLL:
         getattr(L, f"sb_exclusive_carry_{t}").argtypes = [vp, vp, i, vp]
     for t in ("i32", "i64"):
         getattr(L, f"sb_check_iota_{t}").argtypes = [vp, vp, sz, u64, i, sz, vp]
+    for t, ct in (("i32", C.c_int32), ("i64", C.c_int64), ("f32", C.c_float), ("f64", C.c_double)):
+        getattr(L, f"sb_fill_{t}").argtypes = [vp, vp, sz, ct]
     L.sb_host_reduce.argtypes = [vp, i, vp, sz, vp]
     L.sb_host_scan.argtypes = [vp, i, vp, vp, sz, i, sz]
     L.sb_host_segreduce.argtypes = [vp, i, vp, sz, sz]
@@ -199,6 +201,12 @@ class Context:
         t = dtype or dtype_of(out)
         n = out.numel() if n is None else n
         _check(getattr(lib(), f"sb_iota_{t}")(self._h, _ptr(out), n, offset))
+        return out
+
+    def fill(self, out, value, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(out)
+        n = out.numel() if n is None else n
+        _check(getattr(lib(), f"sb_fill_{t}")(self._h, _ptr(out), n, value))
         return out
 
     def reduce(self, x, out, n: Optional[int] = None, dtype: Optional[str] = None):
