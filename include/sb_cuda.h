@@ -118,6 +118,12 @@ int sb_fill_i64(sb_ctx*, int64_t* out, size_t n, int64_t value);
 int sb_fill_f32(sb_ctx*, float* out, size_t n, float value);
 int sb_fill_f64(sb_ctx*, double* out, size_t n, double value);
 
+/* dst[0..bytes) = src[0..bytes), device to device, one launch for 16-byte congruent pointers.  The copy
+ * kernel of micro/DRAM.cpp:54-62 (`out[gid] = in[gid]`, one work-item per element, in a 1-, 2- or 3-D
+ * index space over the same contiguous buffer): the in-suite calibrator for the HBM roofline.
+ * Algorithmic bytes 2 * bytes.  The ranges must not overlap. */
+int sb_copy(sb_ctx*, void* dst, const void* src, size_t bytes);
+
 /* ---- reduction ------------------------------------------------------------------------------ */
 /* out[0] = sum(in[0..n)), one launch.  Replaces the whole multi-pass driver
  * Reduction<T>::submit (pattern/reduction.cpp:71-97) and both kernels
@@ -129,6 +135,24 @@ int sb_reduce_i32(sb_ctx*, const int32_t* in, size_t n, int32_t* out);
 int sb_reduce_i64(sb_ctx*, const int64_t* in, size_t n, int64_t* out);
 int sb_reduce_f32(sb_ctx*, const float* in, size_t n, float* out);
 int sb_reduce_f64(sb_ctx*, const double* in, size_t n, double* out);
+
+/* ---- fused two-input reductions ------------------------------------------ */
+/* out[0] = sum a[i] * b[i], one launch, a and b read once, nothing else written.  Replaces the whole
+ * run() of ScalarProdBench (single-kernel/scalar_prod.cpp:54-175): the product kernel (:55-83), and per
+ * pass the work-group tree kernel (:96-170) and the gather kernel (:172-178) over the product buffer.
+ * Every product is rounded to T before it is added (the reference stores it first); integers wrap. */
+int sb_dot_i32(sb_ctx*, const int32_t* a, const int32_t* b, size_t n, int32_t* out);
+int sb_dot_i64(sb_ctx*, const int64_t* a, const int64_t* b, size_t n, int64_t* out);
+int sb_dot_f32(sb_ctx*, const float* a, const float* b, size_t n, float* out);
+int sb_dot_f64(sb_ctx*, const double* a, const double* b, size_t n, double* out);
+/* Simple linear regression y ~ b0 + b1 x in one launch.  out6 = { sum xy, sum xx, sum x, sum y, b1, b0 }.
+ * Replaces LinearRegressionCoeffBench::run (single-kernel/lin_reg_coeff.cpp:126-146): two vec_product
+ * launches (:52-69), four in-place multi-pass reductions (:71-124) and the host arithmetic (:134-142),
+ * which is reproduced operation for operation in T: mean = sum / n, ss_xy = sum xy - mean_x mean_y,
+ * ss_xx = sum xx - mean_x mean_x, b1 = ss_xy / ss_xx, b0 = mean_y - b1 mean_x.  x and y are NOT modified
+ * (the reference reduces them in place).  n == 0: the sums are 0 and the coefficients NaN. */
+int sb_linreg_f32(sb_ctx*, const float* x, const float* y, size_t n, float* out6);
+int sb_linreg_f64(sb_ctx*, const double* x, const double* y, size_t n, double* out6);
 
 /* ---- segmented reduction -------------------------------------------------------------------- */
 /* In place, reference layout (pattern/segmentedreduction.cpp:35-61,63-96; contract :112-119):

@@ -64,6 +64,11 @@ def lib() -> C.CDLL:
             getattr(L, f"ref2020_kernel_{t}").restype = CT[t]
             getattr(L, f"ref2020_verify_atomic_{t}").argtypes = [CT[t], u64]
             getattr(L, f"ref2020_verify_size_{t}").argtypes = [CT[t], u64]
+        # single-kernel/scalar_prod, lin_reg_coeff (oracle/sb_oracle_single_kernel.c)
+        for t in REF_REDUCTION_TYPES:
+            getattr(L, f"ref_scalar_prod_{t}").argtypes = [vp, vp, sz, sz, vp]
+        for t in ("f32", "f64"):
+            getattr(L, f"ref_linreg_{t}").argtypes = [vp, vp, sz, sz, vp]
         L.kat_reduce.argtypes = [u64]
         L.kat_reduce.restype = u64
         L.kat_scan.argtypes = [u64, i, u64]
@@ -112,6 +117,24 @@ def scan(t: str, x: np.ndarray, exclusive: bool = False, group_len: int = 0, fla
         flags = np.ascontiguousarray(flags, dtype=np.uint8)
         fp = flags.ctypes.data
     getattr(lib(), f"ref_scan_{t}")(x.ctypes.data, out.ctypes.data, x.size, int(exclusive), group_len, fp)
+    return out
+
+
+def scalar_prod(t: str, a: np.ndarray, b: np.ndarray, L: int):
+    """single-kernel/scalar_prod.cpp:54-180 restated (ref_scalar_prod_<t>)."""
+    out = np.zeros(1, dtype=NP[t])
+    rc = getattr(lib(), f"ref_scalar_prod_{t}")(a.ctypes.data, b.ctypes.data, a.size, L, out.ctypes.data)
+    if rc != 0:
+        raise ValueError("ref_scalar_prod: n and L must be positive")
+    return out[0]
+
+
+def linreg(t: str, x: np.ndarray, y: np.ndarray, L: int) -> np.ndarray:
+    """single-kernel/lin_reg_coeff.cpp:126-146 restated: [sum xy, sum xx, sum x, sum y, b1, b0]."""
+    out = np.zeros(6, dtype=NP[t])
+    rc = getattr(lib(), f"ref_linreg_{t}")(x.ctypes.data, y.ctypes.data, x.size, L, out.ctypes.data)
+    if rc != 0:
+        raise ValueError("ref_linreg: n >= 1 and L >= 2")
     return out
 
 

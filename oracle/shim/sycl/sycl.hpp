@@ -341,6 +341,9 @@ public:
   id<D> get_global_id() const { return id<D>(grp * lsize + lid); }
   std::size_t get_global_id(int) const { return grp * lsize + lid; }
   std::size_t get_group(int) const { return grp; }
+  std::size_t get_global_linear_id() const { return grp * lsize + lid; }
+  std::size_t get_local_linear_id() const { return lid; }
+  std::size_t get_group_linear_id() const { return grp; }
   group<D> get_group() const { return group<D>(grp, lsize, ngroups); }
   std::size_t get_local_range(int) const { return lsize; }
 
@@ -511,6 +514,15 @@ public:
 #pragma omp for schedule(static)
       for(std::size_t g = 0; g < G; ++g) f(group<1>(g, L, G));
     }
+  }
+
+  // basic parallel_for(range, f(id)).  Executed in ascending index order on one thread: the only user on the
+  // path, the gather kernel of single-kernel/scalar_prod.cpp:172-178 (`g[idx] = g[idx * L]` for all idx in
+  // parallel), reads elements that other work-items write; ascending order is the schedule under which
+  // every read sees the value of the previous pass.
+  template <typename Name = void, typename F>
+  void parallel_for(range<1> r, F f) {
+    for(std::size_t i = 0; i < r[0]; ++i) f(id<1>(i));
   }
 
   // parallel_for(range, reduction, f(id, reducer&)): one private reducer per OpenMP thread over a static

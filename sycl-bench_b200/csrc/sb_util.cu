@@ -48,6 +48,27 @@ __global__ void __launch_bounds__(UT_NT) fill_kernel(A* __restrict__ out, size_t
   }
 }
 
+// sb_copy: flat grid, one 16 KB chunk per CTA (512 threads x 2 x 16 B, both loads issued before the first
+// store).  The block scheduler hands the chunks out in address order, which keeps the DRAM access front
+// compact: 6.93 TB/s against 5.97 TB/s for a persistent grid-stride loop and 6.58 TB/s for cudaMemcpyAsync
+// device-to-device (profiles/r01_stream_probe.txt).
+constexpr int CP_NT = 512;
+constexpr int CP_U = 2;
+__global__ void __launch_bounds__(CP_NT) copy_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t nvec) {
+  const size_t b = (size_t)blockIdx.x * CP_NT * CP_U + threadIdx.x;
+  uint4 t[CP_U];
+#pragma unroll
+  for(int u = 0; u < CP_U; ++u)
+    if(b + (size_t)u * CP_NT < nvec) t[u] = __ldg(in + b + (size_t)u * CP_NT);
+#pragma unroll
+  for(int u = 0; u < CP_U; ++u)
+    if(b + (size_t)u * CP_NT < nvec) out[b + (size_t)u * CP_NT] = t[u];
+}
+// bytes that the vector body does not cover (head / tail), or everything when src and dst are not congruent mod 16
+__global__ void __launch_bounds__(UT_NT) copy_bytes_kernel(const unsigned char* __restrict__ in, unsigned char* __restrict__ out, size_t n) {
+  for(size_t i = (size_t)blockIdx.x * UT_NT + threadIdx.x; i < n; i += (size_t)gridDim.x * UT_NT) out[i] = in[i];
+}
+
 template <typename A>
 __global__ void __launch_bounds__(UT_NT) carry_add_kernel(A* __restrict__ buf, size_t n, const A* __restrict__ carry, int aligned) {
   constexpr int VEC = 16 / sizeof(A);
@@ -196,6 +217,38 @@ int sb_iota_i32(sb_ctx* c, int32_t* o, size_t n, uint64_t off) { return iota_imp
 int sb_iota_i64(sb_ctx* c, int64_t* o, size_t n, uint64_t off) { return iota_impl<int64_t>(c, o, n, off); }
 int sb_iota_f32(sb_ctx* c, float* o, size_t n, uint64_t off) { return iota_impl<float>(c, o, n, off); }
 int sb_iota_f64(sb_ctx* c, double* o, size_t n, uint64_t off) { return iota_impl<double>(c, o, n, off); }
+int sb_copy(sb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if(!ctx || (bytes && (!dst || !src))) return SB_ERR_BAD_ARG;
+  if(bytes == 0 || dst == src) return SB_OK;
+  sb_device_guard guard(ctx->device);
+  const unsigned char* s = static_cast<const unsigned char*>(src);
+  unsigned char* d = static_cast<unsigned char*>(dst);
+  const uintptr_t sa = reinterpret_cast<uintptr_t>(s) & 15, da = reinterpret_cast<uintptr_t>(d) & 15;
+  if(sa != da) {  // no common 16-byte phase: byte copy
+    copy_bytes_kernel<<<(unsigned)grid_for(ctx, bytes, UT_NT), UT_NT, 0, ctx->stream>>>(s, d, bytes);
+    SB_CHECK_LAUNCH(ctx);
+    return SB_OK;
+  }
+  size_t head = (16 - sa) & 15;
+  if(head > bytes) head = bytes;
+  const size_t nvec = (bytes - head) / 16;
+  const size_t tail = bytes - head - nvec * 16;
+  if(nvec) {
+    const size_t chunks = (nvec + (size_t)CP_NT * CP_U - 1) / ((size_t)CP_NT * CP_U);
+    if(chunks > 0x7fffffffull) return SB_ERR_BAD_ARG;
+    copy_kernel<<<(unsigned)chunks, CP_NT, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(s + head), reinterpret_cast<uint4*>(d + head), nvec);
+    SB_CHECK_LAUNCH(ctx);
+  }
+  if(head) {
+    copy_bytes_kernel<<<1, UT_NT, 0, ctx->stream>>>(s, d, head);
+    SB_CHECK_LAUNCH(ctx);
+  }
+  if(tail) {
+    copy_bytes_kernel<<<1, UT_NT, 0, ctx->stream>>>(s + head + nvec * 16, d + head + nvec * 16, tail);
+    SB_CHECK_LAUNCH(ctx);
+  }
+  return SB_OK;
+}
 int sb_fill_i32(sb_ctx* c, int32_t* o, size_t n, int32_t v) { return fill_impl<int32_t>(c, o, n, v); }
 int sb_fill_i64(sb_ctx* c, int64_t* o, size_t n, int64_t v) { return fill_impl<int64_t>(c, o, n, v); }
 int sb_fill_f32(sb_ctx* c, float* o, size_t n, float v) { return fill_impl<float>(c, o, n, v); }

@@ -95,6 +95,11 @@ def lib() -> C.CDLL:
         getattr(L, f"sb_check_iota_{t}").argtypes = [vp, vp, sz, u64, i, sz, vp]
     for t, ct in (("i32", C.c_int32), ("i64", C.c_int64), ("f32", C.c_float), ("f64", C.c_double)):
         getattr(L, f"sb_fill_{t}").argtypes = [vp, vp, sz, ct]
+    L.sb_copy.argtypes = [vp, vp, vp, sz]
+    for t in ("i32", "i64", "f32", "f64"):
+        getattr(L, f"sb_dot_{t}").argtypes = [vp, vp, vp, sz, vp]
+    for t in ("f32", "f64"):
+        getattr(L, f"sb_linreg_{t}").argtypes = [vp, vp, vp, sz, vp]
     L.sb_host_reduce.argtypes = [vp, i, vp, sz, vp]
     L.sb_host_scan.argtypes = [vp, i, vp, vp, sz, i, sz]
     L.sb_host_segreduce.argtypes = [vp, i, vp, sz, sz]
@@ -214,6 +219,27 @@ class Context:
         n = x.numel() if n is None else n
         _check(getattr(lib(), f"sb_reduce_{t}")(self._h, _ptr(x), n, _ptr(out)))
         return out
+
+    def copy(self, dst, src, nbytes: Optional[int] = None):
+        """dst = src, device to device (the micro/DRAM copy kernel)."""
+        if nbytes is None:
+            nbytes = src.numel() * src.element_size()
+        _check(lib().sb_copy(self._h, _ptr(dst), _ptr(src), nbytes))
+        return dst
+
+    def dot(self, a, b, out, n: Optional[int] = None, dtype: Optional[str] = None):
+        """out[0] = sum a[i] * b[i] (one launch, both inputs read once)."""
+        t = dtype or dtype_of(a)
+        n = a.numel() if n is None else n
+        _check(getattr(lib(), f"sb_dot_{t}")(self._h, _ptr(a), _ptr(b), n, _ptr(out)))
+        return out
+
+    def linreg(self, x, y, out6, n: Optional[int] = None, dtype: Optional[str] = None):
+        """out6 = [sum xy, sum xx, sum x, sum y, b1, b0] (one launch)."""
+        t = dtype or dtype_of(x)
+        n = x.numel() if n is None else n
+        _check(getattr(lib(), f"sb_linreg_{t}")(self._h, _ptr(x), _ptr(y), n, _ptr(out6)))
+        return out6
 
     def scan(self, x, out, exclusive: bool = False, group_len: int = 0, seed=None, n: Optional[int] = None, dtype: Optional[str] = None):
         t = dtype or dtype_of(x)
