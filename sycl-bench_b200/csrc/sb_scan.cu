@@ -42,7 +42,10 @@
 //  carries a per-launch epoch, so descriptors are never reset between launches.  Segmented
 //  variants run the same code on (value, head-flag) pairs: (v1,f1)(+)(v2,f2) = (f2 ? v2 : v1+v2,
 //  f1|f2); if every tile starts on a head (power-of-two segment <= tile) no descriptor is touched.
+#include <cuda.h>
+
 #include <atomic>
+#include <cstdlib>
 
 #include "sb_common.cuh"
 
@@ -619,6 +622,48 @@ scan_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t
   tile_pass2_store<A, MODE, ALIGNED, K>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, exclusive);
 }
 
+// Round look-back with every descriptor load of the round in flight at once (G <= 32 * MAXB): one L2 round
+// trip when the aggregates are there, instead of one per SCAN_WINDOW x 32 descriptors.  The phase trace
+// (profiles/tb_trace.py) showed 2-4.5 us per look-back with the windowed walk — several dependent L2 round
+// trips at ~1 us each under streaming load — which capped the kernel at one tile per ~3.4 us and CTA.
+template <typename A, int MAXB>
+__device__ __forceinline__ A lookback_round_wide(const typename Desc<A>::word* desc, const typename Desc<A>::word* rdesc, long long tile,
+    long long G, uint32_t epoch, const A* __restrict__ seed) {
+  const int lane = sb::lane_id();
+  const long long r = tile / G;
+  const int pos = (int)(tile - r * G);
+  const typename Desc<A>::word* row = desc + r * G;
+  uint32_t rst = (epoch << 2) | ST_INCL;
+  A rval = A(0);
+  if(lane == 0) {
+    if(r > 0) Desc<A>::load(rdesc + (r - 1), rst, rval);
+    else if(seed) rval = *seed;
+  }
+  uint32_t st[MAXB];
+  A val[MAXB];
+#pragma unroll
+  for(int u = 0; u < MAXB; ++u) {
+    const int q = u * 32 + lane;
+    st[u] = (epoch << 2) | ST_AGG;
+    val[u] = A(0);
+    if(q < pos) Desc<A>::load(row + q, st[u], val[u]);
+  }
+  A lane_sum = A(0);
+#pragma unroll
+  for(int u = 0; u < MAXB; ++u) {
+    const int q = u * 32 + lane;
+    if(q < pos) {
+      while((st[u] >> 2) != epoch) Desc<A>::load(row + q, st[u], val[u]);
+    }
+    lane_sum += val[u];
+  }
+  A total = sb::warp_sum<A>(lane_sum);
+  if(lane == 0 && r > 0) {
+    while((rst >> 2) != epoch) Desc<A>::load(rdesc + (r - 1), rst, rval);
+  }
+  return total + sb::shfl_idx(rval, 0);
+}
+
 // ---- kernel 2: persistent, warp-specialised, TMA ring (see header) ---------------------------------------------
 // bytes of one ring stage: the data tile and, for explicit head flags, the tile's flag bytes behind it
 template <typename A, int MODE, int K>
@@ -915,6 +960,247 @@ scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg
   }
 }
 
+// ---- kernel 4: thread-blocked scan through swizzled TMA tensor tiles (global scans, 16-byte aligned) --------
+// The array is viewed as a 2-D tensor of 128-byte rows.  A tile is TB_NW*32 rows; TMA (cp.async.bulk.tensor,
+// SWIZZLE_128B) drops it into the ring so that chunk j of row r sits at chunk j ^ (r & 7): every worker thread
+// owns ONE row = 128 consecutive bytes of the array and reads / rewrites it with eight conflict-free
+// LDS.128 / STS.128.  Per tile a thread does one serial scan of its 32 (16) elements, ONE warp scan of the
+// thread totals and one add per element — about 6x fewer instructions than the row-per-warp kernels above
+// (ncu: 51 warp instructions per 64-bit element there, issue slots 50 % busy).  Results are written back into
+// the same ring stage and leave through a TMA tensor store issued by a dedicated warp, so worker warps issue
+// no global memory instruction at all.  Rows beyond the end of the array are zero-filled on load and clipped
+// on store by the TMA unit: no ragged-tile code.  Warp roles: TB_NW workers, loader, storer, two look-back warps (even / odd tiles of the CTA).
+#ifndef SB_TB_NW
+#define SB_TB_NW 12
+#endif
+#ifndef SB_TB_STAGES
+#define SB_TB_STAGES 3
+#endif
+constexpr int TB_NW = SB_TB_NW, TB_STAGES = SB_TB_STAGES;
+constexpr int TB_ROWS = TB_NW * 32;          // rows (= worker threads) per tile
+constexpr int TB_STAGE_BYTES = TB_ROWS * 128;
+constexpr int TB_BOXES = (TB_ROWS + 255) / 256;  // TMA boxes per tile (box height is limited to 256 rows)
+constexpr int TB_BOX_ROWS = TB_ROWS / TB_BOXES;
+static_assert(TB_BOX_ROWS * TB_BOXES == TB_ROWS && (TB_BOX_ROWS * 128) % 1024 == 0, "tile does not split into swizzle-aligned boxes");
+constexpr int TB_THREADS = (TB_NW + 4) * 32;  // workers, loader, storer, two look-back warps
+
+// optional phase trace (-DSB_TB_TRACE): %globaltimer stamps of the first TB_TRACE_TILES tiles of every CTA
+#ifdef SB_TB_TRACE
+constexpr int TB_TRACE_TILES = 48, TB_TRACE_EVENTS = 16;
+__device__ unsigned long long tb_trace[160][TB_TRACE_TILES][TB_TRACE_EVENTS];
+__device__ __forceinline__ void tb_stamp(long long tile_i, int ev) {
+  if(tile_i < TB_TRACE_TILES && blockIdx.x < 160) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tb_trace[blockIdx.x][tile_i][ev] = t;
+  }
+}
+#define TB_STAMP(i, ev) tb_stamp(i, ev)
+#else
+#define TB_STAMP(i, ev)
+#endif
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
+template <typename A>
+__global__ void __launch_bounds__(TB_THREADS, 1)
+scan_tb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, long long total_rows, int exclusive,
+    const A* __restrict__ seed, typename Desc<A>::word* desc, typename Desc<A>::word* total_slot, uint32_t epoch, long long num_tiles) {
+  constexpr int E = 128 / sizeof(A);   // elements per row / thread
+  constexpr int VEC = 16 / sizeof(A);  // elements per 16-byte chunk
+  extern __shared__ unsigned char tb_raw[];
+  __shared__ __align__(8) unsigned long long full_bar[TB_STAGES], empty_bar[TB_STAGES], stored_bar, out_free_bar, agg_bar[2], prefix_bar[2];
+  __shared__ A s_wagg[2][TB_NW], s_wprefix[2][TB_NW];
+
+  const uint32_t ring = (smem_u32(tb_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte aligned tiles
+  const uint32_t out_tile = ring + TB_STAGES * TB_STAGE_BYTES;  // staging tile of the TMA store
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long G = gridDim.x;
+  const long long my_tiles = (num_tiles - (long long)blockIdx.x + G - 1) / G;
+
+  if(threadIdx.x == 0) {
+#pragma unroll
+    for(int s = 0; s < TB_STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), TB_NW);
+    }
+    mbar_init(smem_u32(&stored_bar), TB_NW);
+    mbar_init(smem_u32(&out_free_bar), 1);
+#pragma unroll
+    for(int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&agg_bar[s]), TB_NW);
+      mbar_init(smem_u32(&prefix_bar[s]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();  // the only block-wide barrier
+
+  if(warp == TB_NW) {
+    // ===== loader: TMA tensor loads into the ring; a stage is free again as soon as the workers hold it in registers =====
+    if(lane != 0) return;
+    for(long long i = 0; i < my_tiles; ++i) {
+      const int stage = (int)(i % TB_STAGES);
+      if(i >= TB_STAGES) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)((i / TB_STAGES) - 1) & 1u);
+      const long long row0 = ((long long)blockIdx.x + i * G) * TB_ROWS;
+      const uint32_t bar = smem_u32(&full_bar[stage]);
+      int boxes = 0;
+#pragma unroll
+      for(int h = 0; h < TB_BOXES; ++h) boxes += (row0 + h * TB_BOX_ROWS < total_rows) ? 1 : 0;
+      TB_STAMP(i, 0);  // load issue
+      mbar_expect_tx(bar, (uint32_t)boxes * TB_BOX_ROWS * 128u);
+#pragma unroll
+      for(int h = 0; h < TB_BOXES; ++h)
+        if(row0 + h * TB_BOX_ROWS < total_rows) tma_load_2d(ring + stage * TB_STAGE_BYTES + h * TB_BOX_ROWS * 128, &tm_in, 0, (int)(row0 + h * TB_BOX_ROWS), bar);
+    }
+  } else if(warp == TB_NW + 1 || warp == TB_NW + 3) {
+    // ===== look-back warps (one for the even, one for the odd tiles of this CTA, so that consecutive look-backs
+    // overlap): tile aggregate -> descriptor, round look-back, per-warp prefixes for the workers =====
+    const typename Desc<A>::word* rdesc = desc + num_tiles;
+    for(long long i = (warp == TB_NW + 1) ? 0 : 1; i < my_tiles; i += 2) {
+      const int slot = (int)(i & 1);
+      const long long tile = (long long)blockIdx.x + i * G;
+      mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(i >> 1) & 1u);
+      if(lane == 0) TB_STAMP(i, 1);  // aggregates of all warps in
+      const A mine = lane < TB_NW ? s_wagg[slot][lane] : A(0);
+      A incl = mine;
+#pragma unroll
+      for(int d = 1; d < 32; d <<= 1) {
+        const A up = sb::shfl_up(incl, d);
+        if(lane >= d) incl += up;
+      }
+      const A tile_agg = sb::shfl_idx(incl, 31);
+      if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | ST_AGG, tile_agg);
+      const A p = G <= 160 ? lookback_round_wide<A, 5>(desc, rdesc, tile, G, epoch, seed) : lookback_round<A, MODE_PLAIN>(desc, rdesc, tile, G, epoch, seed);
+      if(lane == 0 && (tile + 1) % G == 0)
+        Desc<A>::store(const_cast<typename Desc<A>::word*>(rdesc) + tile / G, (epoch << 2) | ST_INCL, p + tile_agg);
+      if(lane == 0 && tile == num_tiles - 1) Desc<A>::store(total_slot, (epoch << 2) | ST_INCL, p + tile_agg);  // for the tail kernel
+      if(lane < TB_NW) s_wprefix[slot][lane] = p + (incl - mine);
+      __syncwarp();
+      if(lane == 0) TB_STAMP(i, 2);  // look-back done
+      if(lane == 0) mbar_arrive(smem_u32(&prefix_bar[slot]));
+    }
+  } else if(warp == TB_NW + 2) {
+    // ===== storer: TMA tensor store of the staging tile =====
+    if(lane != 0) return;
+    for(long long i = 0; i < my_tiles; ++i) {
+      mbar_wait(smem_u32(&stored_bar), (uint32_t)i & 1u);
+      TB_STAMP(i, 3);  // all rows written to the staging tile
+      const long long row0 = ((long long)blockIdx.x + i * G) * TB_ROWS;
+#pragma unroll
+      for(int h = 0; h < TB_BOXES; ++h)
+        if(row0 + h * TB_BOX_ROWS < total_rows) tma_store_2d(&tm_out, out_tile + h * TB_BOX_ROWS * 128, 0, (int)(row0 + h * TB_BOX_ROWS));
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging tile has been read
+      TB_STAMP(i, 4);  // staging tile free
+      mbar_arrive(smem_u32(&out_free_bar));
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores have landed before the CTA retires
+  } else {
+    // ===== workers: thread t owns row t of every tile.  Software pipeline over two register sets:
+    //   phase A(k+1): ring -> registers (the stage goes straight back to the loader), serial row scan, warp scan
+    //                 of the row totals, warp aggregate to the look-back warp
+    //   phase B(k)  : wait for the tile prefix (it has had a whole tile time to arrive), add, write the row to
+    //                 the staging tile, hand it to the storer.
+    const uint32_t row_off = (uint32_t)threadIdx.x * 128u;
+    const uint32_t sw = (uint32_t)(threadIdx.x & 7);
+    auto phase_a = [&](long long k, A (&x)[E], A& thread_excl) {
+      const int stage = (int)(k % TB_STAGES), slot = (int)(k & 1);
+      const uint32_t row = ring + stage * TB_STAGE_BYTES + row_off;
+      const bool valid = ((long long)blockIdx.x + k * G) * TB_ROWS + threadIdx.x < total_rows;
+      if(threadIdx.x == 0) TB_STAMP(k, 5);  // phase A: start waiting for the data
+      mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(k / TB_STAGES) & 1u);
+      if(threadIdx.x == 0) TB_STAMP(k, 6);  // data there
+#pragma unroll
+      for(int j = 0; j < 8; ++j) {
+        uint4 q;
+        const uint32_t addr = row + (((uint32_t)j ^ sw) << 4);
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr) : "memory");
+        const sb::Vec<A>& t = *reinterpret_cast<const sb::Vec<A>*>(&q);
+#pragma unroll
+        for(int c = 0; c < VEC; ++c) x[j * VEC + c] = valid ? t.v[c] : A(0);  // rows behind the end of the array count as zeros
+      }
+      // serial inclusive scan of the row (left to right: the order of a sequential scan)
+#pragma unroll
+      for(int e = 1; e < E; ++e) x[e] += x[e - 1];
+      __syncwarp();
+      if(lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));  // the warp's rows live in registers now
+      A incl = x[E - 1];
+#pragma unroll
+      for(int d = 1; d < 32; d <<= 1) {
+        const A up = sb::shfl_up(incl, d);
+        if(lane >= d) incl += up;
+      }
+      thread_excl = incl - x[E - 1];
+      if(lane == 31) {
+        s_wagg[slot][warp] = incl;
+        mbar_arrive(smem_u32(&agg_bar[slot]));
+      }
+      if(threadIdx.x == 0) TB_STAMP(k, 7);  // phase A done
+    };
+    auto phase_b = [&](long long k, A (&x)[E], A thread_excl) {
+      const int slot = (int)(k & 1);
+      if(threadIdx.x == 0) TB_STAMP(k, 8);  // phase B: waiting for the prefix
+      mbar_wait(smem_u32(&prefix_bar[slot]), (uint32_t)(k >> 1) & 1u);
+      if(threadIdx.x == 0) TB_STAMP(k, 9);  // prefix there
+      const A add = s_wprefix[slot][warp] + thread_excl;
+      if(exclusive) {
+#pragma unroll
+        for(int e = E - 1; e > 0; --e) x[e] = x[e - 1] + add;
+        x[0] = add;
+      } else {
+#pragma unroll
+        for(int e = 0; e < E; ++e) x[e] += add;
+      }
+      if(k > 0) mbar_wait(smem_u32(&out_free_bar), (uint32_t)(k - 1) & 1u);  // the store of tile k-1 has read the staging tile
+#pragma unroll
+      for(int j = 0; j < 8; ++j) {
+        sb::Vec<A> t;
+#pragma unroll
+        for(int c = 0; c < VEC; ++c) t.v[c] = x[j * VEC + c];
+        const uint32_t addr = out_tile + row_off + (((uint32_t)j ^ sw) << 4);
+        const uint4& q = *reinterpret_cast<const uint4*>(&t);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the rows visible to the TMA store
+      __syncwarp();
+      if(threadIdx.x == 0) TB_STAMP(k, 10);  // phase B done
+      if(lane == 0) mbar_arrive(smem_u32(&stored_bar));
+    };
+    A xa[E], xb[E];
+    A ea = A(0), eb = A(0);
+    if(my_tiles > 0) phase_a(0, xa, ea);
+    for(long long k = 0; k < my_tiles; k += 2) {
+      if(k + 1 < my_tiles) phase_a(k + 1, xb, eb);
+      phase_b(k, xa, ea);
+      if(k + 1 < my_tiles) {
+        if(k + 2 < my_tiles) phase_a(k + 2, xa, ea);
+        phase_b(k + 1, xb, eb);
+      }
+    }
+  }
+}
+
+// elements behind the last full 128-byte row (fewer than 128 / sizeof(A)); runs after scan_tb_kernel on the stream
+template <typename A>
+__global__ void scan_tb_tail_kernel(const A* in, A* out, size_t n_main, size_t n, int exclusive, const typename Desc<A>::word* total_slot) {
+  if(threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t st;
+  A run;
+  Desc<A>::load(total_slot, st, run);  // seed + sum of the first n_main elements (in and out may be the same buffer)
+  for(size_t i = n_main; i < n; ++i) {
+    const A x = in[i];
+    if(exclusive) out[i] = run;
+    run += x;
+    if(!exclusive) out[i] = run;
+  }
+}
+
 // co-resident CTAs per SM of a persistent kernel instantiation.  The shared-memory opt-in is a per-device
 // function attribute, so the query (and the opt-in) is made once per device, on the current device.
 constexpr int SB_MAX_DEVICES = 64;
@@ -971,6 +1257,59 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
   return SB_OK;
 }
 
+// ---- host side of kernel 4: tensor maps + cooperative launch ---------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// [rows][128 bytes] view of a 16-byte aligned array, box = 256 rows, 128-byte swizzle
+bool make_row_map(CUtensorMap* tm, const void* base, unsigned long long rows) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if(!enc) return false;
+  const cuuint64_t dims[2] = {32, rows};          // 32 x u32 = 128 bytes per row
+  const cuuint64_t strides[1] = {128};            // bytes between rows
+  const cuuint32_t box[2] = {32, TB_BOX_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// returns SB_ERR_UNSUPPORTED when the tensor-map path is not available (caller falls back to scan_ws_kernel)
+template <typename A>
+int launch_tb(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, const A* seed, typename Desc<A>::word* desc, uint32_t epoch, size_t tiles) {
+  constexpr size_t E = 128 / sizeof(A);
+  const unsigned long long rows = n / E;
+  if(rows == 0 || rows >= 0xffffffffull) return SB_ERR_UNSUPPORTED;
+  alignas(64) CUtensorMap tm_in, tm_out;
+  if(!make_row_map(&tm_in, in, rows) || !make_row_map(&tm_out, out, rows)) return SB_ERR_UNSUPPORTED;
+  constexpr size_t smem = (size_t)(TB_STAGES + 1) * TB_STAGE_BYTES + 1024;  // ring + staging tile + alignment slack
+  static OccupancyCache cache;
+  const int per_sm = resident_ctas_per_sm(cache, ctx->device, scan_tb_kernel<A>, TB_THREADS, smem);
+  if(per_sm <= 0) return SB_ERR_UNSUPPORTED;
+  const long long num_tiles = (long long)((rows + TB_ROWS - 1) / TB_ROWS);
+  size_t grid = (size_t)ctx->sm_count;  // one CTA per SM (launch bounds)
+  if((long long)grid > num_tiles) grid = (size_t)num_tiles;
+  long long total_rows = (long long)rows;
+  typename Desc<A>::word* total_slot = desc + 2 * tiles + 32;  // scratch behind the tile and round descriptors
+  void* args[] = {(void*)&tm_in, (void*)&tm_out, (void*)&total_rows, (void*)&exclusive, (void*)&seed, (void*)&desc, (void*)&total_slot, (void*)&epoch, (void*)&num_tiles};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_tb_kernel<A>, dim3((unsigned)grid), dim3(TB_THREADS), args, smem, ctx->stream);
+  if(e != cudaSuccess) return (int)e;
+  const size_t n_main = (size_t)rows * E;
+  if(n_main < n) {
+    ctx->launches++;
+    scan_tb_tail_kernel<A><<<1, 32, 0, ctx->stream>>>(in, out, n_main, n, exclusive, total_slot);
+  }
+  return SB_OK;
+}
+
 template <typename T>
 int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int mode, size_t seg_len, const uint8_t* flags, const T* seed) {
   using A = typename sb_arith<T>::type;
@@ -1021,6 +1360,17 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   const A* aseed = reinterpret_cast<const A*>(seed);
   if(use_ws) {
     int rc;
+    // global scans: SB_SCAN_TB=1 selects the experimental thread-blocked kernel on swizzled TMA tensor tiles
+    // (parity-green, currently slower than the row-per-warp kernel: DESIGN.md section 4.4)
+    static const bool tb_enabled = getenv("SB_SCAN_TB") && getenv("SB_SCAN_TB")[0] == '1';
+    if(mode == MODE_PLAIN && use_lookback && tb_enabled) {
+      rc = launch_tb<A>(ctx, ain, aout, n, exclusive, aseed, desc, epoch, tiles);
+      if(rc == SB_OK) {
+        SB_CHECK_LAUNCH(ctx);
+        return SB_OK;
+      }
+      if(rc != SB_ERR_UNSUPPORTED) return rc;
+    }
     if(mode == MODE_PLAIN) rc = launch_ws<A, MODE_PLAIN>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT) rc = launch_ws<A, MODE_IMPLICIT>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else rc = launch_ws<A, MODE_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
@@ -1060,6 +1410,12 @@ int segscan_impl(sb_ctx* ctx, const T* in, T* out, size_t n, size_t seg_len, con
 }
 
 }  // namespace
+
+#ifdef SB_TB_TRACE
+extern "C" __attribute__((visibility("default"))) int sb_tb_trace_dump(unsigned long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, tb_trace, sizeof(tb_trace));
+}
+#endif
 
 size_t sb_scan_tile_bytes() { return (size_t)WS_NW * WS_K * 512; }
 

@@ -475,3 +475,49 @@ def test_host_api_chunked_pipeline(ctx, O, t):
     assert_close(t, buf, O.segreduce(t, hx[:m], 256), m, "chunked segreduce")
     ctx.host_segscan(hx, res, seg_len=4096)
     assert_close(t, res, O.scan(t, hx, False, 4096), n, "chunked segscan")
+
+
+# ---------------------------------------------------------------------------------------------- experimental kernel
+def test_thread_blocked_scan_kernel_parity():
+    """SB_SCAN_TB=1 selects scan_tb_kernel (swizzled TMA tensor tiles, thread-blocked rows, TMA store).  The switch
+    is read once per process, so the check runs in a subprocess: integer scans bit-exact against the closed form
+    on the device, fp32 / fp64 against the sequential fp64 scan within the tolerance, ragged sizes, exclusive,
+    in place, seeded."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path.insert(0, %r)
+        import __graft_entry__ as ge
+        pkg = ge.load_package()
+        ctx = pkg.Context(0, torch.cuda.current_stream().cuda_stream)
+        TD = {"i32": torch.int32, "i64": torch.int64, "f32": torch.float32, "f64": torch.float64}
+        for t in ("i32", "i64"):
+            for n in (1 << 20, (1 << 22) + 12345, (1 << 24) + 7):
+                for excl in (False, True):
+                    x = torch.empty(n, dtype=TD[t], device="cuda"); y = torch.empty_like(x)
+                    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+                    ctx.iota(x); ctx.scan(x, y, exclusive=excl); ctx.check_iota(y, bad, kind=1 if excl else 0); ctx.sync()
+                    assert int(bad.cpu()[0]) == 0, (t, n, excl)
+                    ctx.scan(x, x, exclusive=excl); ctx.sync()          # in place
+                    assert torch.equal(x, y), (t, n, excl, "in place")
+        rng = np.random.default_rng(5)
+        for t, tol in (("f32", 1e-5), ("f64", 1e-12)):
+            n = (1 << 21) + 1001
+            h = (rng.random(n) * 2 - 1).astype(np.float32 if t == "f32" else np.float64)
+            x = torch.from_numpy(h).cuda(); y = torch.empty_like(x)
+            seed = torch.full((1,), 3.5, dtype=TD[t], device="cuda")
+            ctx.scan(x, y, seed=seed); ctx.sync()
+            want = np.cumsum(h.astype(np.float64)) + 3.5
+            # forward error bound of a summation: relative to the running sum of magnitudes (the values cancel)
+            err = np.abs(y.cpu().numpy().astype(np.float64) - want) / (np.cumsum(np.abs(h.astype(np.float64))) + 3.5)
+            assert err.max() <= tol * np.log2(n), (t, err.max())
+        print("TB-OK", ctx.launches)
+    """ % root)
+    env = dict(os.environ, SB_SCAN_TB="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "TB-OK" in r.stdout, r.stdout + r.stderr
