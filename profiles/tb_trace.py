@@ -1,10 +1,13 @@
-"""Phase trace of scan_tb_kernel (build with -DSB_TB_TRACE): per-tile time stamps of CTA roles.
+"""Phase trace of scan_tb_kernel: per-tile %globaltimer stamps of the CTA roles.
 
+    make -C sycl-bench_b200 trace        # lib/tune/libsb_cuda_trace.so, sb_scan.cu compiled with -DSB_TB_TRACE
     SB_CUDA_LIB=sycl-bench_b200/lib/tune/libsb_cuda_trace.so python profiles/tb_trace.py [dtype] [log2n]
 """
 import ctypes as C
 import os
 import sys
+
+os.environ.setdefault("SB_SCAN_TB", "1")  # the traced kernel is behind this switch (read when the library loads)
 
 import numpy as np
 import torch
