@@ -76,6 +76,10 @@ int sb_ctx_sync(sb_ctx* ctx);
 /* device-name CSV column: include/common.h:42-43. */
 int sb_ctx_device_name(sb_ctx* ctx, char* buf, size_t buflen);
 int sb_ctx_sm_count(sb_ctx* ctx);
+/* PCI bus id of the ctx device ("0000:1b:00.0"): lets a caller find the same device in NVML, whose indices
+ * ignore CUDA_VISIBLE_DEVICES (used by the harness's energy / clock hook, the reference's empty
+ * include/nv_energy_meas.h). */
+int sb_ctx_pci_bus_id(sb_ctx* ctx, char* buf, size_t buflen);
 /* Number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 uint64_t sb_ctx_launch_count(sb_ctx* ctx);
 /* on != 0: floating-point sb_reduce_* uses a fixed summation order (bit-reproducible run to run,

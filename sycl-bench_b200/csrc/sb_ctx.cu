@@ -144,6 +144,12 @@ int sb_ctx_device_name(sb_ctx* ctx, char* buf, size_t buflen) {
   return SB_OK;
 }
 
+int sb_ctx_pci_bus_id(sb_ctx* ctx, char* buf, size_t buflen) {
+  if(!ctx || !buf || buflen < 16) return SB_ERR_BAD_ARG;
+  SB_CUDA_TRY(cudaDeviceGetPCIBusId(buf, (int)buflen, ctx->device));
+  return SB_OK;
+}
+
 int sb_ctx_set_deterministic(sb_ctx* ctx, int on) {
   if(!ctx) return SB_ERR_BAD_ARG;
   ctx->deterministic = on != 0;

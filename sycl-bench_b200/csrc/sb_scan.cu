@@ -80,8 +80,15 @@ constexpr int SCAN_NT = SB_SCAN_NT;
 constexpr int SCAN_K = SB_SCAN_K;
 constexpr int SCAN_WINDOW = SB_SCAN_WINDOW;
 constexpr int WS_NW = SB_WS_NW, WS_K = SB_WS_K, WS_STAGES = SB_WS_STAGES, WS_DEPTH = SB_WS_DEPTH;
+#ifndef SB_WS_NW_WIDE
+#define SB_WS_NW_WIDE 18  // worker warps of the 72 KB-tile instantiations (global scans; 32-bit independent tiles)
+#endif
+constexpr int WS_NW_WIDE = SB_WS_NW_WIDE;
+#ifndef SB_WS_NW_NARROW
+#define SB_WS_NW_NARROW 15  // 15 workers + producer = 16 warps: 128 registers per thread for 64-bit independent tiles
+#endif
+constexpr int WS_NW_NARROW = SB_WS_NW_NARROW;
 constexpr int WS_NSLOT = 2 * WS_DEPTH + 2;  // a fast warp is at most DEPTH+1 tiles ahead of a slow one
-constexpr int WS_THREADS = (WS_NW + 2) * 32;
 
 enum : uint32_t { ST_AGG = 1u, ST_INCL = 2u };
 enum { MODE_PLAIN = 0, MODE_IMPLICIT = 1, MODE_FLAGS = 2 };
@@ -666,19 +673,18 @@ __device__ __forceinline__ A lookback_round_wide(const typename Desc<A>::word* d
 
 // ---- kernel 2: persistent, warp-specialised, TMA ring (see header) ---------------------------------------------
 // bytes of one ring stage: the data tile and, for explicit head flags, the tile's flag bytes behind it
-template <typename A, int MODE, int K>
+template <typename A, int MODE, int K, int NW>
 __host__ __device__ constexpr int ws_stage_bytes() {
-  return TileCfg<A, WS_NW, K>::TILE_BYTES + (MODE == MODE_FLAGS ? TileCfg<A, WS_NW, K>::TILE : 0);
+  return TileCfg<A, NW, K>::TILE_BYTES + (MODE == MODE_FLAGS ? TileCfg<A, NW, K>::TILE : 0);
 }
 
-template <typename A, int MODE, int K>
-__global__ void __launch_bounds__(WS_THREADS, SB_WS_MINB)
+template <typename A, int MODE, int K, int NW>
+__global__ void __launch_bounds__((NW + 2) * 32, SB_WS_MINB)
 scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
     const A* __restrict__ seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, long long num_tiles, int flags_in_ring) {
-  using C = TileCfg<A, WS_NW, K>;
+  using C = TileCfg<A, NW, K>;
   constexpr int VEC = C::VEC;
-  constexpr int NW = WS_NW;
-  constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K>();
+  constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K, NW>();
   extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x STAGE_BYTES
   __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES], agg_bar[WS_NSLOT], prefix_bar[WS_NSLOT];
   __shared__ A s_wagg[WS_NSLOT][NW];
@@ -869,14 +875,13 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
 // always published before it asks — so the look-back kernel above keeps static assignment.
 constexpr int WS_TILE_IDS = 8;  // ring of tile ids handed from the producer to the workers
 
-template <typename A, int MODE, int K>
-__global__ void __launch_bounds__((WS_NW + 1) * 32, SB_WS_MINB)
+template <typename A, int MODE, int K, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, SB_WS_MINB)
 scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
     long long num_tiles, int flags_in_ring, unsigned long long* ticket, unsigned long long ticket_base) {
-  using C = TileCfg<A, WS_NW, K>;
+  using C = TileCfg<A, NW, K>;
   constexpr int VEC = C::VEC;
-  constexpr int NW = WS_NW;
-  constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K>();
+  constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K, NW>();
   extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x STAGE_BYTES
   __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES], agg_bar[WS_NSLOT];
   __shared__ A s_wagg[WS_NSLOT][NW];
@@ -1224,27 +1229,28 @@ int resident_ctas_per_sm(OccupancyCache& cache, int device, Kern kern, int threa
 // rows per worker warp: 8 (64 KB tiles); 6 with explicit flags so that 3 stages of data + flag bytes fit in 227 KB
 template <int MODE> struct ws_rows { static constexpr int K = MODE == MODE_FLAGS ? (WS_K * 3) / 4 : WS_K; };
 
-template <typename A, int MODE>
+template <typename A, int MODE, int NW>
 int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* flags,
     const A* seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, size_t tiles) {
   constexpr int K = ws_rows<MODE>::K;
-  constexpr size_t smem = (size_t)WS_STAGES * ws_stage_bytes<A, MODE, K>();
+  constexpr size_t smem = (size_t)WS_STAGES * ws_stage_bytes<A, MODE, K, NW>();
+  constexpr int WS_THREADS = (NW + 2) * 32;
   static OccupancyCache ws_cache, ind_cache;
-  const int per_sm = resident_ctas_per_sm(ws_cache, ctx->device, scan_ws_kernel<A, MODE, K>, WS_THREADS, smem);
+  const int per_sm = resident_ctas_per_sm(ws_cache, ctx->device, scan_ws_kernel<A, MODE, K, NW>, WS_THREADS, smem);
   if(per_sm <= 0) return SB_ERR_WORKSPACE;
   size_t grid = (size_t)ctx->sm_count * per_sm;
   if(grid > tiles) grid = tiles;
   int flags_in_ring = (MODE == MODE_FLAGS && sb::aligned_to(flags, 16)) ? 1 : 0;  // TMA needs 16-byte aligned sources
   long long num_tiles = (long long)tiles;
   if(!use_lookback) {
-    const int ind_per_sm = resident_ctas_per_sm(ind_cache, ctx->device, scan_independent_kernel<A, MODE, K>, (WS_NW + 1) * 32, smem);
+    const int ind_per_sm = resident_ctas_per_sm(ind_cache, ctx->device, scan_independent_kernel<A, MODE, K, NW>, (NW + 1) * 32, smem);
     if(ind_per_sm <= 0) return SB_ERR_WORKSPACE;
     size_t g = (size_t)ctx->sm_count * ind_per_sm;
     if(g > tiles) g = tiles;
     // every CTA's producer draws tickets until one is past the last tile: tiles + grid tickets per launch
     const unsigned long long tbase = ctx->scan_ticket_base;
     ctx->scan_ticket_base += tiles + g;
-    scan_independent_kernel<A, MODE, K><<<(unsigned)g, (WS_NW + 1) * 32, smem, ctx->stream>>>(in, out, n, exclusive, seg_len, seg_mask, flags,
+    scan_independent_kernel<A, MODE, K, NW><<<(unsigned)g, (NW + 1) * 32, smem, ctx->stream>>>(in, out, n, exclusive, seg_len, seg_mask, flags,
         num_tiles, flags_in_ring, ctx->scan_ticket, tbase);
     return SB_OK;
   }
@@ -1252,7 +1258,7 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
   // launch) — the forward-progress condition of the static round-robin look-back.  No grid barrier is used.
   void* args[] = {(void*)&in, (void*)&out, (void*)&n, (void*)&exclusive, (void*)&seg_len, (void*)&seg_mask, (void*)&flags, (void*)&seed,
       (void*)&desc, (void*)&epoch, (void*)&use_lookback, (void*)&num_tiles, (void*)&flags_in_ring};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_ws_kernel<A, MODE, K>, dim3((unsigned)grid), dim3(WS_THREADS), args, smem, ctx->stream);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_ws_kernel<A, MODE, K, NW>, dim3((unsigned)grid), dim3(WS_THREADS), args, smem, ctx->stream);
   if(e != cudaSuccess) return (int)e;
   return SB_OK;
 }
@@ -1321,7 +1327,16 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
 
   // persistent kernel for 16-byte aligned buffers with at least a few tiles; ticketed kernel otherwise
   const bool aligned = sb::aligned_to(in, 16) && sb::aligned_to(out, 16);
-  const size_t ws_tile = mode == MODE_FLAGS ? TileCfg<A, WS_NW, ws_rows<MODE_FLAGS>::K>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
+  // 18 worker warps (72 KB tiles) where they measured faster: global scans, whose rate is tile bytes per look-back
+  // round, and 32-bit independent tiles; 16 warps (64 KB) everywhere else
+  constexpr size_t wide_tile = TileCfg<A, WS_NW_WIDE, WS_K>::TILE;
+  const bool wide = mode == MODE_PLAIN || (mode == MODE_IMPLICIT && sizeof(A) == 4 && sb::is_pow2(seg_len) && wide_tile % seg_len == 0);
+  // 64-bit independent tiles: 15 workers, so that the CTA is 16 warps and a thread may use 128 registers — at 17
+  // warps ptxas has 96 and spills (fp64 group scan 5.5 -> 6.4 TB/s)
+  constexpr size_t narrow_tile = TileCfg<A, WS_NW_NARROW, WS_K>::TILE;
+  const bool narrow = mode == MODE_IMPLICIT && sizeof(A) == 8 && sb::is_pow2(seg_len) && narrow_tile % seg_len == 0;
+  const size_t ws_tile = mode == MODE_FLAGS ? TileCfg<A, WS_NW, ws_rows<MODE_FLAGS>::K>::TILE
+                         : wide ? wide_tile : narrow ? narrow_tile : TileCfg<A, WS_NW, WS_K>::TILE;
   const size_t simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
   const bool use_ws = aligned && n >= 4 * ws_tile;
   const size_t tile = use_ws ? ws_tile : simple_tile;
@@ -1371,9 +1386,11 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
       }
       if(rc != SB_ERR_UNSUPPORTED) return rc;
     }
-    if(mode == MODE_PLAIN) rc = launch_ws<A, MODE_PLAIN>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
-    else if(mode == MODE_IMPLICIT) rc = launch_ws<A, MODE_IMPLICIT>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
-    else rc = launch_ws<A, MODE_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    if(mode == MODE_PLAIN) rc = launch_ws<A, MODE_PLAIN, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else if(mode == MODE_IMPLICIT && wide) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else if(mode == MODE_IMPLICIT && narrow) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_NARROW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else if(mode == MODE_IMPLICIT) rc = launch_ws<A, MODE_IMPLICIT, WS_NW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else rc = launch_ws<A, MODE_FLAGS, WS_NW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     if(rc != SB_OK) return rc;
     SB_CHECK_LAUNCH(ctx);
     return SB_OK;

@@ -285,6 +285,8 @@ private:
   std::uint64_t before_ = 0, last_ = 0;
 };
 
+#include "nv_energy_meas.h"  // NvmlEnergyHook (needs BenchmarkHook and ResultConsumer from above)
+
 // ------------------------------------------------------------------------------------------------------------
 // traits
 namespace detail {
@@ -559,6 +561,11 @@ public:
       BenchmarkManager<Benchmark> mgr(args);
       LaunchCountHook launches(args.ctx());
       mgr.addHook(launches);
+      std::unique_ptr<NvmlEnergyHook> nvml;  // energy / clocks / throttle reasons; --no-nvml switches it off
+      if(!args.cli.isFlagSet("--no-nvml")) {
+        nvml = std::make_unique<NvmlEnergyHook>(args.ctx());
+        mgr.addHook(*nvml);
+      }
       if(!mgr.run(extra...)) ++failures;
     } catch(std::exception& e) {
       ++failures;

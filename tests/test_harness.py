@@ -106,6 +106,22 @@ def test_stdio_consumer():
 
 
 @pytest.mark.gpu
+def test_nvml_energy_hook_columns(tmp_path):
+    """harness/nv_energy_meas.h (the reference's empty include/nv_energy_meas.h): clock / power / throttle columns
+    from NVML, matched to the CUDA device by PCI bus id; --no-nvml removes them."""
+    table, _ = _run("reduction", tmp_path, "--size=268435456", "--num-runs=20")
+    for row in table.values():
+        assert float(row["sm-clock-mhz"]) > 0 and float(row["sm-clock-max-mhz"]) >= float(row["sm-clock-mhz"])
+        assert float(row["power-w"]) > 0
+        assert row["throttle-reasons"] == "none" or all(p in ("gpu_idle", "applications_clocks_setting", "sw_power_cap", "hw_slowdown", "sync_boost",
+                                                              "sw_thermal_slowdown", "hw_thermal_slowdown", "hw_power_brake_slowdown",
+                                                              "display_clock_setting") for p in row["throttle-reasons"].split("|"))
+    os.remove(tmp_path / "reduction.csv")
+    table, _ = _run("reduction", tmp_path, "--size=65536", "--num-runs=1", "--no-nvml")
+    assert all("sm-clock-mhz" not in row for row in table.values())
+
+
+@pytest.mark.gpu
 def test_run_suite_quicktest(tmp_path):
     out = tmp_path / "suite.csv"
     r = subprocess.run([os.path.join(ROOT, "sycl-bench_b200", "run-suite"), "quicktest", f"--output={out}"], capture_output=True, text=True, timeout=600)
