@@ -88,6 +88,10 @@ constexpr int WS_NW_WIDE = SB_WS_NW_WIDE;
 #define SB_WS_NW_NARROW 15  // 15 workers + producer = 16 warps: 128 registers per thread for 64-bit independent tiles
 #endif
 constexpr int WS_NW_NARROW = SB_WS_NW_NARROW;
+#ifndef SB_WS_NW_FLAGS
+#define SB_WS_NW_FLAGS SB_WS_NW  // worker warps of the explicit-flag instantiation
+#endif
+constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
 constexpr int WS_NSLOT = 2 * WS_DEPTH + 2;  // a fast warp is at most DEPTH+1 tiles ahead of a slow one
 
 enum : uint32_t { ST_AGG = 1u, ST_INCL = 2u };
@@ -1335,7 +1339,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   // warps ptxas has 96 and spills (fp64 group scan 5.5 -> 6.4 TB/s)
   constexpr size_t narrow_tile = TileCfg<A, WS_NW_NARROW, WS_K>::TILE;
   const bool narrow = mode == MODE_IMPLICIT && sizeof(A) == 8 && sb::is_pow2(seg_len) && narrow_tile % seg_len == 0;
-  const size_t ws_tile = mode == MODE_FLAGS ? TileCfg<A, WS_NW, ws_rows<MODE_FLAGS>::K>::TILE
+  const size_t ws_tile = mode == MODE_FLAGS ? TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS>::K>::TILE
                          : wide ? wide_tile : narrow ? narrow_tile : TileCfg<A, WS_NW, WS_K>::TILE;
   const size_t simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
   const bool use_ws = aligned && n >= 4 * ws_tile;
@@ -1390,7 +1394,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
     else if(mode == MODE_IMPLICIT && wide) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && narrow) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_NARROW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT) rc = launch_ws<A, MODE_IMPLICIT, WS_NW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
-    else rc = launch_ws<A, MODE_FLAGS, WS_NW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     if(rc != SB_OK) return rc;
     SB_CHECK_LAUNCH(ctx);
     return SB_OK;
