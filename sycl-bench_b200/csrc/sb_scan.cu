@@ -1044,7 +1044,7 @@ scan_tb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #pragma unroll
     for(int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&agg_bar[s]), TB_NW);
-      mbar_init(smem_u32(&prefix_bar[s]), 1);
+      mbar_init(smem_u32(&prefix_bar[s]), TB_NW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1089,10 +1089,11 @@ scan_tb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       if(lane == 0 && (tile + 1) % G == 0)
         Desc<A>::store(const_cast<typename Desc<A>::word*>(rdesc) + tile / G, (epoch << 2) | ST_INCL, p + tile_agg);
       if(lane == 0 && tile == num_tiles - 1) Desc<A>::store(total_slot, (epoch << 2) | ST_INCL, p + tile_agg);  // for the tail kernel
-      if(lane < TB_NW) s_wprefix[slot][lane] = p + (incl - mine);
-      __syncwarp();
       if(lane == 0) TB_STAMP(i, 2);  // look-back done
-      if(lane == 0) mbar_arrive(smem_u32(&prefix_bar[slot]));
+      if(lane < TB_NW) {  // every writer releases its own value: the barrier counts TB_NW arrivals
+        s_wprefix[slot][lane] = p + (incl - mine);
+        mbar_arrive(smem_u32(&prefix_bar[slot]));
+      }
     }
   } else if(warp == TB_NW + 2) {
     // ===== storer: TMA tensor store of the staging tile =====
@@ -1146,6 +1147,7 @@ scan_tb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         if(lane >= d) incl += up;
       }
       thread_excl = incl - x[E - 1];
+      __syncwarp();  // every lane is past its read of s_wprefix[slot] (phase B of tile k-2) before the slot is re-armed
       if(lane == 31) {
         s_wagg[slot][warp] = incl;
         mbar_arrive(smem_u32(&agg_bar[slot]));
