@@ -59,7 +59,7 @@ namespace {
 #define SB_SCAN_K 4  // ticketed kernel: rows per warp
 #endif
 #ifndef SB_SCAN_WINDOW
-#define SB_SCAN_WINDOW 4  // look-back: batches of 32 descriptors polled per step
+#define SB_SCAN_WINDOW 5  // look-back: batches of 32 descriptors polled per step (5 x 32 covers a whole round of 148 tiles)
 #endif
 #ifndef SB_WS_NW
 #define SB_WS_NW 16  // persistent kernel: worker warps
@@ -213,13 +213,25 @@ __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, 
       val[u] = A(0);
       if(q >= 0) Desc<A>::load(row + q, st[u], val[u]);
     }
+    // Poll until every descriptor of the window is there, re-issuing ALL missing loads of a pass back to back: one
+    // L2 round trip per pass.  (Waiting for them one after the other cost up to U + 1 dependent round trips of
+    // ~1.1 us each under load — the phase trace showed look-backs of 4-8 us after the last aggregate was out.)
+    for(;;) {
+      bool missing = false;
+#pragma unroll
+      for(int u = 0; u < U; ++u) {
+        const int q = hi - 1 - (u * 32 + lane);
+        if(q >= 0 && (st[u] >> 2) != epoch) {
+          missing = true;
+          Desc<A>::load(row + q, st[u], val[u]);
+        }
+      }
+      if(lane == 0 && r > 0 && (rst >> 2) != epoch) Desc<A>::load(rdesc + (r - 1), rst, rval);  // keep the round prefix polling too
+      if(!__any_sync(SB_FULL_MASK, missing)) break;
+    }
 #pragma unroll
     for(int u = 0; u < U; ++u) {
       if(head_found) break;
-      const int q = hi - 1 - (u * 32 + lane);
-      if(q >= 0) {
-        while((st[u] >> 2) != epoch) Desc<A>::load(row + q, st[u], val[u]);
-      }
       if(MODE != MODE_PLAIN) {
         const unsigned heads = __ballot_sync(SB_FULL_MASK, (st[u] & 3u) == ST_INCL);
         if(heads) {
@@ -659,19 +671,27 @@ __device__ __forceinline__ A lookback_round_wide(const typename Desc<A>::word* d
     val[u] = A(0);
     if(q < pos) Desc<A>::load(row + q, st[u], val[u]);
   }
+  // one L2 round trip per polling pass: every missing descriptor (and the round prefix) is re-requested at once
+  for(;;) {
+    bool missing = false;
+#pragma unroll
+    for(int u = 0; u < MAXB; ++u) {
+      const int q = u * 32 + lane;
+      if(q < pos && (st[u] >> 2) != epoch) {
+        missing = true;
+        Desc<A>::load(row + q, st[u], val[u]);
+      }
+    }
+    if(lane == 0 && r > 0 && (rst >> 2) != epoch) {
+      missing = true;
+      Desc<A>::load(rdesc + (r - 1), rst, rval);
+    }
+    if(!__any_sync(SB_FULL_MASK, missing)) break;
+  }
   A lane_sum = A(0);
 #pragma unroll
-  for(int u = 0; u < MAXB; ++u) {
-    const int q = u * 32 + lane;
-    if(q < pos) {
-      while((st[u] >> 2) != epoch) Desc<A>::load(row + q, st[u], val[u]);
-    }
-    lane_sum += val[u];
-  }
-  A total = sb::warp_sum<A>(lane_sum);
-  if(lane == 0 && r > 0) {
-    while((rst >> 2) != epoch) Desc<A>::load(rdesc + (r - 1), rst, rval);
-  }
+  for(int u = 0; u < MAXB; ++u) lane_sum += val[u];
+  const A total = sb::warp_sum<A>(lane_sum);
   return total + sb::shfl_idx(rval, 0);
 }
 
