@@ -389,6 +389,15 @@ __device__ __forceinline__ void warp_reduce_rows(const A (&v)[K][16 / sizeof(A)]
     has_head = false;
     return;
   }
+  {
+    unsigned any = 0;
+#pragma unroll
+    for(int j = 0; j < K; ++j) any |= hf[j];
+    if(!__any_sync(SB_FULL_MASK, any != 0u)) {  // no head in the warp chunk: one warp sum instead of K
+      warp_reduce_rows<A, MODE_PLAIN, K>(v, hf, agg, has_head);
+      return;
+    }
+  }
   A run = A(0);
   bool runf = false;
 #pragma unroll
@@ -468,6 +477,15 @@ template <typename A, int MODE, int K>
 __device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A (&carry_in)[K], bool (&open)[K],
     A& warp_agg, bool& warp_has_head) {
   if(MODE != MODE_PLAIN) {
+    // a warp chunk without any head (the common case once segments are longer than K rows) is a plain scan:
+    // take the unchained path, whose K row scans are independent shuffle chains
+    unsigned any = 0;
+#pragma unroll
+    for(int j = 0; j < K; ++j) any |= hf[j];
+    if(!__any_sync(SB_FULL_MASK, any != 0u)) {
+      tile_pass1<A, MODE_PLAIN, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+      return;
+    }
     tile_pass1_chained<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
     return;
   }
