@@ -209,9 +209,10 @@ int sb_comm_reduce(sb_comm* c, int dtype, const void* const* in, const size_t* n
   }
   if(c->n > 1) {
     if(nccl().GroupStart() != ncclSuccess) return SB_ERR_NCCL;
-    for(int r = 0; r < c->n; ++r)
-      if(nccl().AllReduce(out[r], out[r], 1, nccl_type(dtype), ncclSum, c->comms[r], c->ctx[r]->stream) != ncclSuccess) return SB_ERR_NCCL;
-    if(nccl().GroupEnd() != ncclSuccess) return SB_ERR_NCCL;
+    bool ok = true;
+    for(int r = 0; r < c->n && ok; ++r)
+      ok = nccl().AllReduce(out[r], out[r], 1, nccl_type(dtype), ncclSum, c->comms[r], c->ctx[r]->stream) == ncclSuccess;
+    if(nccl().GroupEnd() != ncclSuccess || !ok) return SB_ERR_NCCL;  // the group is always closed
   }
   return sb_comm_join(c);
 }
@@ -244,9 +245,10 @@ int sb_comm_scan(sb_comm* c, int dtype, const void* const* in, void* const* out,
   }
   // 2. one element per rank crosses NVLink
   if(nccl().GroupStart() != ncclSuccess) return SB_ERR_NCCL;
-  for(int r = 0; r < c->n; ++r)
-    if(nccl().AllGather(carry(r), totals(r), 1, nccl_type(dtype), c->comms[r], c->ctx[r]->stream) != ncclSuccess) return SB_ERR_NCCL;
-  if(nccl().GroupEnd() != ncclSuccess) return SB_ERR_NCCL;
+  bool ok = true;
+  for(int r = 0; r < c->n && ok; ++r)
+    ok = nccl().AllGather(carry(r), totals(r), 1, nccl_type(dtype), c->comms[r], c->ctx[r]->stream) == ncclSuccess;
+  if(nccl().GroupEnd() != ncclSuccess || !ok) return SB_ERR_NCCL;  // the group is always closed
   // 3. exclusive carry on the device, then the seeded scan / the carry-add pass
   for(int r = 0; r < c->n; ++r) {
     int rc = excl_carry_call(c->ctx[r], dtype, totals(r), r, carry(r));
