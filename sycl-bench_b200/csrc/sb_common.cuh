@@ -150,6 +150,36 @@ __device__ __forceinline__ T shfl_up(T v, int d) { return __shfl_up_sync(SB_FULL
 template <typename T>
 __device__ __forceinline__ T shfl_idx(T v, int l) { return __shfl_sync(SB_FULL_MASK, v, l); }
 
+// One step of an inclusive warp scan: x += (value of lane - d), only in lanes >= d.  shfl.sync.up returns a
+// predicate that says whether the source lane exists, so the add is predicated directly: no compare, no select
+// (ncu on the scan kernel: SEL 18 % + ISETP 8 % of all executed instructions with the `if(lane >= d)` form).
+template <int D> __device__ __forceinline__ void scan_step_up(uint32_t& x) {
+  asm volatile("{.reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t;}" : "+r"(x) : "n"(D));
+}
+template <int D> __device__ __forceinline__ void scan_step_up(float& x) {
+  asm volatile("{.reg .pred p; .reg .f32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.rn.f32 %0, %0, t;}" : "+f"(x) : "n"(D));
+}
+template <int D> __device__ __forceinline__ void scan_step_up(unsigned long long& x) {
+  asm volatile(
+      "{.reg .pred p; .reg .u32 lo, hi, tlo, thi; .reg .u64 t; mov.b64 {lo, hi}, %0;"
+      " shfl.sync.up.b32 tlo|p, lo, %1, 0, 0xffffffff; shfl.sync.up.b32 thi, hi, %1, 0, 0xffffffff;"
+      " mov.b64 t, {tlo, thi}; @p add.u64 %0, %0, t;}" : "+l"(x) : "n"(D));
+}
+template <int D> __device__ __forceinline__ void scan_step_up(double& x) {
+  asm volatile(
+      "{.reg .pred p; .reg .u32 lo, hi, tlo, thi; .reg .f64 t; mov.b64 {lo, hi}, %0;"
+      " shfl.sync.up.b32 tlo|p, lo, %1, 0, 0xffffffff; shfl.sync.up.b32 thi, hi, %1, 0, 0xffffffff;"
+      " mov.b64 t, {tlo, thi}; @p add.rn.f64 %0, %0, t;}" : "+d"(x) : "n"(D));
+}
+// inclusive warp scan (plain sum) built from the five steps
+template <typename T> __device__ __forceinline__ void warp_inclusive_scan(T& x) {
+  scan_step_up<1>(x);
+  scan_step_up<2>(x);
+  scan_step_up<4>(x);
+  scan_step_up<8>(x);
+  scan_step_up<16>(x);
+}
+
 inline bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 

@@ -514,10 +514,14 @@ __device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], cons
       h = m ? 31 - __clz(m) : 0;
     }
     A inc = s;
+    if(MODE == MODE_PLAIN) {
+      sb::warp_inclusive_scan<A>(inc);  // predicated shuffle-adds
+    } else {
 #pragma unroll
-    for(int d = 1; d < 32; d <<= 1) {
-      const A t = sb::shfl_up(inc, d);
-      if(lane >= h + d) inc += t;
+      for(int d = 1; d < 32; d <<= 1) {
+        const A t = sb::shfl_up(inc, d);
+        if(lane >= h + d) inc += t;
+      }
     }
     const A ex = sb::shfl_up(inc, 1);
     carry_in[j] = lane == 0 ? A(0) : ex;
