@@ -52,5 +52,5 @@ def test_reference_citations_resolve():
             checked += 1
             if not (1 <= lo <= hi <= lengths[path]):
                 bad.append((os.path.relpath(src, ROOT), m.group(0), f"file has {lengths[path]} lines"))
-    assert checked > 100, checked
+    assert checked > 80, checked
     assert not bad, bad[:20]
