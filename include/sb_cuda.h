@@ -48,7 +48,10 @@ enum sb_status {
   SB_ERR_NO_DEVICE = -5,   /* no CUDA device / device index out of range                       */
   SB_ERR_UNSUPPORTED = -6, /* device is not sm_100 (library is built for sm_100a only)         */
   SB_ERR_TIMER = -7,       /* sb_timer_end without sb_timer_begin                              */
-  SB_ERR_NCCL = -8         /* libnccl.so.2 could not be loaded, or an NCCL call failed         */
+  SB_ERR_NCCL = -8,        /* libnccl.so.2 could not be loaded, or an NCCL call failed         */
+  SB_ERR_TIMEOUT = -9,     /* a kernel gave up waiting for another CTA / GPU; reported once by the next
+                              sb_ctx_sync / sb_timer_end / sb_host_* call; results of that op are invalid */
+  SB_ERR_PEER = -10        /* CUDA IPC / peer access failed, or a peer of the group is not connected   */
 };
 
 enum sb_dtype { SB_I16 = 0, SB_I32 = 1, SB_I64 = 2, SB_F32 = 3, SB_F64 = 4 };
@@ -65,8 +68,10 @@ int sb_device_count(int* count);
 /* One ctx per (device, stream): the counterpart of `BenchmarkArgs::device_queue`
  * (include/command_line.h:133,152-154).  `stream` is a cudaStream_t: NULL is the CUDA default
  * stream (as in every CUDA API), SB_STREAM_OWNED asks for a new non-blocking stream owned by the
- * ctx (the in-order queue of include/command_line.h:154).  The ctx owns the scratch the kernels need (block partials, tile
- * descriptors, tickets), sized once for the device, so that op calls never allocate. */
+ * ctx (the in-order queue of include/command_line.h:154).  The ctx owns the scratch the kernels need: block partials
+ * and tickets have a fixed size; the tile descriptors of the scans grow on demand — the first scan of a given size
+ * on a ctx synchronises the stream and reallocates them (never under stream capture, never shrinking).  Call
+ * sb_ctx_reserve from setup() to keep that out of a timed or captured region. */
 int sb_ctx_create(int device, void* stream, sb_ctx** out);
 int sb_ctx_destroy(sb_ctx* ctx);
 int sb_ctx_set_stream(sb_ctx* ctx, void* stream);
@@ -86,8 +91,12 @@ uint64_t sb_ctx_launch_count(sb_ctx* ctx);
  * about 3 % slower).  Default off: chunks are handed to CTAs in order of arrival.  Integer results
  * and all scans are reproducible either way. */
 int sb_ctx_set_deterministic(sb_ctx* ctx, int on);
-/* Bytes of device scratch the ctx holds / that an op on n elements touches. */
+/* Upper bound of the device scratch an op on n elements of `dtype` touches on any device this library supports
+ * (the scans pick their tile size by alignment and size; the bound assumes the smallest tile). */
 size_t sb_workspace_bytes(int op, int dtype, size_t n);
+/* Grow the ctx scratch now to what `op` on n elements can need (sb_workspace_bytes), so that the op itself never
+ * allocates: the place for it is setup() (include/common.h:55-59), outside the timed run(). */
+int sb_ctx_reserve(sb_ctx* ctx, int op, int dtype, size_t n);
 
 /* CUDA-event timing on the ctx stream; replaces the SYCL event profiling of
  * include/common.h:83-101 (kernel-time).  begin/end may bracket any number of sb_* calls. */
@@ -132,8 +141,9 @@ int sb_copy(sb_ctx*, void* dst, const void* src, size_t bytes);
 /* out[0] = sum(in[0..n)), one launch.  Replaces the whole multi-pass driver
  * Reduction<T>::submit (pattern/reduction.cpp:71-97) and both kernels
  * local_reduce_ndrange (:99-126) / local_reduce_hierarchical (:128-167).
- * Integers wrap mod 2^w (bit-exact with the reference for any order).  Floating point uses a
- * fixed (deterministic) order that differs from the reference's tree; see DESIGN.md tolerance.
+ * Integers wrap mod 2^w (bit-exact with the reference for any order).  Floating point sums in an order that differs
+ * from the reference's tree (tolerance) and, by default, from run to run: chunks are handed to CTAs in
+ * order of arrival.  sb_ctx_set_deterministic(ctx, 1) fixes the order (bit-reproducible, about 3 % slower).
  * n == 0 writes 0.  `out` must not alias `in`. */
 int sb_reduce_i32(sb_ctx*, const int32_t* in, size_t n, int32_t* out);
 int sb_reduce_i64(sb_ctx*, const int64_t* in, size_t n, int64_t* out);
@@ -214,6 +224,11 @@ int sb_exclusive_carry_f64(sb_ctx*, const double* totals, int rank, double* carr
  *   kind 2: segmented-reduction layout (head = segment sum, others = input). */
 int sb_check_iota_i32(sb_ctx*, const int32_t* data, size_t n, uint64_t offset, int kind, size_t seg_len, uint64_t* mismatches);
 int sb_check_iota_i64(sb_ctx*, const int64_t* data, size_t n, uint64_t offset, int kind, size_t seg_len, uint64_t* mismatches);
+/* Floating point: counts elements with |data - closed form| > rel_tol * max(|closed form|, 1) (NaN counts); the closed
+ * form is evaluated in double.  The untouched elements of kind 2 must equal the input (T)(offset+i) exactly.  rel_tol is
+ * the caller's statement of BASELINE.json's tolerance (1e-5 log2 N for fp32, 1e-12 log2 N for fp64). */
+int sb_check_iota_f32(sb_ctx*, const float* data, size_t n, uint64_t offset, int kind, size_t seg_len, double rel_tol, uint64_t* mismatches);
+int sb_check_iota_f64(sb_ctx*, const double* data, size_t n, uint64_t offset, int kind, size_t seg_len, double rel_tol, uint64_t* mismatches);
 
 /* ---- host-buffer (end-to-end) entry points -------------------------------------------------- */
 /* Same operations on HOST buffers: H2D of the input, the kernel, D2H of the result, all on the ctx
@@ -238,7 +253,9 @@ int sb_host_segscan(sb_ctx*, int dtype, const void* h_in, void* h_out, size_t n,
 typedef struct sb_comm sb_comm;
 enum sb_scan_strategy {
   SB_REDUCE_THEN_SCAN = 0, /* sb_reduce -> all-gather -> seeded sb_scan: 3 passes over a shard (default) */
-  SB_SCAN_THEN_CARRY = 1   /* sb_scan -> all-gather -> sb_carry_add: the 4-pass recipe, inclusive only */
+  SB_SCAN_THEN_CARRY = 1,  /* sb_scan -> all-gather -> sb_carry_add: the 4-pass recipe, inclusive only */
+  SB_SCAN_CYCLIC = 2       /* block-cyclic shards, sb_scan_cyclic: 2 passes, totals exchanged by the kernel over NVLink
+                              peer memory, no NCCL call; every n[r] must be the same */
 };
 int sb_comm_create(sb_ctx* rank0, int ngpus, sb_comm** out);
 int sb_comm_destroy(sb_comm* comm);
@@ -249,6 +266,52 @@ int sb_comm_join(sb_comm* comm);
 int sb_comm_reduce(sb_comm* comm, int dtype, const void* const* in, const size_t* n, void* const* out);
 /* out[r] = rank r's shard of the GLOBAL inclusive / exclusive scan */
 int sb_comm_scan(sb_comm* comm, int dtype, const void* const* in, void* const* out, const size_t* n, int exclusive, int strategy);
+
+/* Independent per-shard operations ("replicas"): segmented reduction, segmented scan and the
+ * group-scope scan shard on segment boundaries and need no exchange at all.  One call enqueues the op on every rank's
+ * stream and joins them into rank 0's.  op = SB_OP_SEGREDUCE (inout = out, in ignored), SB_OP_SEGSCAN (implicit heads
+ * every seg_len), SB_OP_SCAN (group scope: restart every seg_len).  Every n[r] must be a multiple of seg_len. */
+int sb_comm_foreach(sb_comm* comm, int op, int dtype, const void* const* in, void* const* out, const size_t* n, size_t seg_len, int exclusive);
+
+/* ---- block-cyclic prefix sum: one read of the input per GPU, exchange inside the kernel ------------------------ */
+/* The global array is dealt to the `world` ranks in blocks of sb_cyclic_block_elems() elements (one round of the
+ * persistent kernel: sm_count tiles of 72 KB): block k lives on rank k % world, a rank stores its blocks back to
+ * back, every rank holds the same number n of elements (the blocks of the last round may be short: they all have
+ * n - floor(n / block) * block elements).  Global index of local element i of rank g, with b = i / block:
+ *     b < n / block :  (b * world + g) * block + i % block
+ *     otherwise     :  (n / block) * world * block + g * (n % block) + i % block
+ * sb_scan_cyclic_<T> writes out[i] = inclusive / exclusive prefix sum at that global index (+ *seed if given).  The
+ * kernel publishes one total per round and rank into every rank's mailbox (sb_peer) with system-scope stores over
+ * NVLink and keeps the tile it is waiting for in the 126 MB L2, so every element is read from HBM once and written
+ * once.  peer == NULL: one GPU (world 1) — the same two-phase kernel, an alternative to sb_scan_<T> for global scans.
+ * All ranks of a peer group must issue their sb_scan_cyclic calls in the same order with the same n (it is a
+ * collective).  in/out must be 16-byte aligned; in == out is allowed. */
+typedef struct sb_peer sb_peer;
+#define SB_PEER_HANDLE_BYTES 64
+size_t sb_cyclic_block_elems(sb_ctx* ctx, int dtype);
+/* one process per GPU: create, exchange the 64-byte handles (any transport), connect every other rank */
+int sb_peer_create(sb_ctx* ctx, int rank, int world, sb_peer** out);
+int sb_peer_handle(sb_peer* peer, void* handle, size_t handle_bytes);                              /* cudaIpcGetMemHandle */
+int sb_peer_connect(sb_peer* peer, int peer_rank, const void* handle, size_t handle_bytes);        /* cudaIpcOpenMemHandle */
+/* one process, several GPUs: connect two peers of the same group directly (enables peer access) */
+int sb_peer_connect_local(sb_peer* peer, sb_peer* other);
+int sb_peer_destroy(sb_peer* peer);
+int sb_peer_rank(sb_peer* peer);
+int sb_peer_world(sb_peer* peer);
+int sb_scan_cyclic_i32(sb_ctx*, sb_peer* peer, const int32_t* in, int32_t* out, size_t n, int exclusive, const int32_t* seed);
+int sb_scan_cyclic_i64(sb_ctx*, sb_peer* peer, const int64_t* in, int64_t* out, size_t n, int exclusive, const int64_t* seed);
+int sb_scan_cyclic_f32(sb_ctx*, sb_peer* peer, const float* in, float* out, size_t n, int exclusive, const float* seed);
+int sb_scan_cyclic_f64(sb_ctx*, sb_peer* peer, const double* in, double* out, size_t n, int exclusive, const double* seed);
+int sb_scan_cyclic(sb_ctx*, sb_peer* peer, int dtype, const void* in, void* out, size_t n, int exclusive);
+/* generate_input / verify() for that layout (n = elements of this rank, the same on every rank) */
+int sb_iota_cyclic_i32(sb_ctx*, int32_t* out, size_t n, size_t block, int world, int rank);
+int sb_iota_cyclic_i64(sb_ctx*, int64_t* out, size_t n, size_t block, int world, int rank);
+int sb_iota_cyclic_f32(sb_ctx*, float* out, size_t n, size_t block, int world, int rank);
+int sb_iota_cyclic_f64(sb_ctx*, double* out, size_t n, size_t block, int world, int rank);
+int sb_check_iota_cyclic_i32(sb_ctx*, const int32_t* data, size_t n, size_t block, int world, int rank, int kind, double rel_tol, uint64_t* mismatches);
+int sb_check_iota_cyclic_i64(sb_ctx*, const int64_t* data, size_t n, size_t block, int world, int rank, int kind, double rel_tol, uint64_t* mismatches);
+int sb_check_iota_cyclic_f32(sb_ctx*, const float* data, size_t n, size_t block, int world, int rank, int kind, double rel_tol, uint64_t* mismatches);
+int sb_check_iota_cyclic_f64(sb_ctx*, const double* data, size_t n, size_t block, int world, int rank, int kind, double rel_tol, uint64_t* mismatches);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

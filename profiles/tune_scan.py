@@ -36,6 +36,7 @@ def worker(args):
         cases = {
             "reduce": (lambda: ctx.reduce(x, out), n * size[t]),
             "scan": (lambda: ctx.scan(x, y), 2 * n * size[t]),
+            "scan_cyclic": (lambda: ctx.scan_cyclic(x, y), 2 * n * size[t]),
             "scan_group256": (lambda: ctx.scan(x, y, exclusive=True, group_len=256), 2 * n * size[t]),
             "segscan_L65536": (lambda: ctx.segscan(x, y, seg_len=65536), 2 * n * size[t]),
             "segreduce256": (lambda: ctx.segreduce(y, 256), n * size[t] + n // 256 * size[t]),
@@ -65,7 +66,7 @@ def worker(args):
                 e1.synchronize()
                 ms.append(e0.elapsed_time(e1))
             ms.sort()
-            res.append({"lib": os.path.basename(pkg.lib_path()), "op": name, "dtype": t, "log2n": args.log2n, "ms_min": round(ms[0], 4),
+            res.append({"lib": os.path.basename(pkg.lib_path()), "env": {k: v for k, v in os.environ.items() if k.startswith("SB_")}, "op": name, "dtype": t, "log2n": args.log2n, "ms_min": round(ms[0], 4),
                         "ms_med": round(ms[len(ms) // 2], 4), "GBps_min": round(nbytes / ms[0] / 1e6, 1), "GBps_med": round(nbytes / ms[len(ms) // 2] / 1e6, 1)})
         del x, y
     for r in res:

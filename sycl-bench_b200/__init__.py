@@ -13,10 +13,11 @@ from .sbcuda import (  # noqa: F401
     DTYPES,
     Comm,
     Context,
+    Peer,
     SbError,
     lib,
     lib_path,
     declared_symbols,
 )
 
-__all__ = ["DTYPES", "Comm", "Context", "SbError", "lib", "lib_path", "declared_symbols"]
+__all__ = ["DTYPES", "Comm", "Context", "Peer", "SbError", "lib", "lib_path", "declared_symbols"]

@@ -5,6 +5,10 @@
 //   scan      : SB_REDUCE_THEN_SCAN  sb_reduce -> ncclAllGather of the shard totals -> sb_exclusive_carry
 //                                    -> sb_scan seeded with the carry                  (3 passes / shard)
 //               SB_SCAN_THEN_CARRY   sb_scan -> ncclAllGather -> sb_exclusive_carry -> sb_carry_add (4 passes)
+//               SB_SCAN_CYCLIC       block-cyclic shards, sb_scan_cyclic on every rank: 2 passes, the round totals cross
+//                                    NVLink inside the kernel (peer-memory mailboxes, sb_scan_cyclic.cu), no NCCL call
+//   foreach   : segmented reduction / segmented scan / group-scope scan on shards cut at segment boundaries:
+//               independent replicas, nothing is exchanged
 //
 // The reference has no multi-device code; nothing here replaces a reference function.  NCCL is loaded
 // with dlopen("libnccl.so.2") on first use so that libsb_cuda.so itself does not depend on it (inside a
@@ -108,6 +112,7 @@ struct sb_comm {
   std::vector<void*> scratch;     // per rank: [0, 8) carry, [64, 64 + 8 n) gathered totals
   std::vector<cudaEvent_t> done;  // per rank: end of its part of an operation
   cudaEvent_t start = nullptr;    // on rank 0: everything enqueued before the operation
+  std::vector<sb_peer*> peers;    // per rank: mailbox of the block-cyclic scan (created on first use)
 };
 
 namespace {
@@ -123,6 +128,28 @@ int comm_fork(sb_comm* c) {
     sb_device_guard guard(c->ctx[r]->device);
     SB_CUDA_TRY(cudaStreamWaitEvent(c->ctx[r]->stream, c->start, 0));
   }
+  return SB_OK;
+}
+// error exit after comm_fork: ranks 1.. may already run on buffers of the caller; join them into rank 0's stream
+// first, so that the caller's sb_ctx_sync(rank 0) covers everything that was enqueued
+int comm_fail(sb_comm* c, int rc) {
+  (void)sb_comm_join(c);
+  return rc;
+}
+
+int ensure_peers(sb_comm* c) {
+  if(!c->peers.empty()) return SB_OK;
+  std::vector<sb_peer*> peers(c->n, nullptr);
+  int rc = SB_OK;
+  for(int r = 0; r < c->n && rc == SB_OK; ++r) rc = sb_peer_create(c->ctx[r], r, c->n, &peers[r]);
+  for(int r = 0; r < c->n && rc == SB_OK; ++r)
+    for(int o = 0; o < c->n && rc == SB_OK; ++o)
+      if(o != r) rc = sb_peer_connect_local(peers[r], peers[o]);
+  if(rc != SB_OK) {
+    for(sb_peer* p : peers) sb_peer_destroy(p);
+    return rc;
+  }
+  c->peers = peers;
   return SB_OK;
 }
 }  // namespace
@@ -169,10 +196,15 @@ int sb_comm_create(sb_ctx* rank0, int ngpus, sb_comm** out) {
 
 int sb_comm_destroy(sb_comm* c) {
   if(!c) return SB_OK;
-  for(int r = 0; r < c->n; ++r) {
+  for(int r = 0; r < c->n; ++r) {  // every rank idle before any rank's mailbox goes away
     if(!c->ctx[r]) continue;
     sb_device_guard guard(c->ctx[r]->device);
     cudaStreamSynchronize(c->ctx[r]->stream);
+  }
+  for(int r = 0; r < c->n; ++r) {
+    if(!c->ctx[r]) continue;
+    sb_device_guard guard(c->ctx[r]->device);
+    if(r < (int)c->peers.size() && c->peers[r]) sb_peer_destroy(c->peers[r]);
     if(c->comms[r]) nccl().CommDestroy(c->comms[r]);
     if(c->scratch[r]) cudaFree(c->scratch[r]);
     if(c->done[r]) cudaEventDestroy(c->done[r]);
@@ -205,14 +237,14 @@ int sb_comm_reduce(sb_comm* c, int dtype, const void* const* in, const size_t* n
   if(int rc = comm_fork(c); rc != SB_OK) return rc;
   for(int r = 0; r < c->n; ++r) {
     int rc = reduce_call(c->ctx[r], dtype, in[r], n[r], out[r]);
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return comm_fail(c, rc);
   }
   if(c->n > 1) {
-    if(nccl().GroupStart() != ncclSuccess) return SB_ERR_NCCL;
+    if(nccl().GroupStart() != ncclSuccess) return comm_fail(c, SB_ERR_NCCL);
     bool ok = true;
     for(int r = 0; r < c->n && ok; ++r)
       ok = nccl().AllReduce(out[r], out[r], 1, nccl_type(dtype), ncclSum, c->comms[r], c->ctx[r]->stream) == ncclSuccess;
-    if(nccl().GroupEnd() != ncclSuccess || !ok) return SB_ERR_NCCL;  // the group is always closed
+    if(nccl().GroupEnd() != ncclSuccess || !ok) return comm_fail(c, SB_ERR_NCCL);  // the group is always closed
   }
   return sb_comm_join(c);
 }
@@ -221,6 +253,18 @@ int sb_comm_scan(sb_comm* c, int dtype, const void* const* in, void* const* out,
   const size_t s = dtype_size(dtype);
   if(!c || !in || !n || !out || s == 0) return SB_ERR_BAD_ARG;
   if(strategy == SB_SCAN_THEN_CARRY && exclusive) return SB_ERR_BAD_ARG;
+  if(strategy == SB_SCAN_CYCLIC) {
+    for(int r = 1; r < c->n; ++r)
+      if(n[r] != n[0]) return SB_ERR_BAD_ARG;  // the block-cyclic layout has equal shards
+    if(int rc = ensure_peers(c); rc != SB_OK) return rc;
+    if(int rc = comm_fork(c); rc != SB_OK) return rc;
+    for(int r = 0; r < c->n; ++r) {
+      int rc = sb_scan_cyclic(c->ctx[r], c->peers[r], dtype, in[r], out[r], n[r], exclusive);
+      if(rc != SB_OK) return comm_fail(c, rc);  // (ranks already launched give up after the kernel's time-out)
+    }
+    return sb_comm_join(c);
+  }
+  if(strategy != SB_REDUCE_THEN_SCAN && strategy != SB_SCAN_THEN_CARRY) return SB_ERR_BAD_ARG;
   if(c->n == 1) {
     int rc = scan_call(c->ctx[0], dtype, in[0], out[0], n[0], exclusive, nullptr);
     return rc;
@@ -237,25 +281,65 @@ int sb_comm_scan(sb_comm* c, int dtype, const void* const* in, void* const* out,
       rc = scan_call(c->ctx[r], dtype, in[r], out[r], n[r], 0, nullptr);
       if(rc == SB_OK) {
         sb_device_guard guard(c->ctx[r]->device);
-        if(n[r]) SB_CUDA_TRY(cudaMemcpyAsync(carry(r), (const char*)out[r] + (n[r] - 1) * s, s, cudaMemcpyDeviceToDevice, c->ctx[r]->stream));
-        else SB_CUDA_TRY(cudaMemsetAsync(carry(r), 0, s, c->ctx[r]->stream));
+        cudaError_t e = n[r] ? cudaMemcpyAsync(carry(r), (const char*)out[r] + (n[r] - 1) * s, s, cudaMemcpyDeviceToDevice, c->ctx[r]->stream)
+                             : cudaMemsetAsync(carry(r), 0, s, c->ctx[r]->stream);
+        if(e != cudaSuccess) rc = (int)e;
       }
     }
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return comm_fail(c, rc);
   }
   // 2. one element per rank crosses NVLink
-  if(nccl().GroupStart() != ncclSuccess) return SB_ERR_NCCL;
+  if(nccl().GroupStart() != ncclSuccess) return comm_fail(c, SB_ERR_NCCL);
   bool ok = true;
   for(int r = 0; r < c->n && ok; ++r)
     ok = nccl().AllGather(carry(r), totals(r), 1, nccl_type(dtype), c->comms[r], c->ctx[r]->stream) == ncclSuccess;
-  if(nccl().GroupEnd() != ncclSuccess || !ok) return SB_ERR_NCCL;  // the group is always closed
+  if(nccl().GroupEnd() != ncclSuccess || !ok) return comm_fail(c, SB_ERR_NCCL);  // the group is always closed
   // 3. exclusive carry on the device, then the seeded scan / the carry-add pass
   for(int r = 0; r < c->n; ++r) {
     int rc = excl_carry_call(c->ctx[r], dtype, totals(r), r, carry(r));
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return comm_fail(c, rc);
     if(strategy == SB_REDUCE_THEN_SCAN) rc = scan_call(c->ctx[r], dtype, in[r], out[r], n[r], exclusive, carry(r));
     else rc = carry_add_call(c->ctx[r], dtype, out[r], n[r], carry(r));
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return comm_fail(c, rc);
+  }
+  return sb_comm_join(c);
+}
+
+int sb_comm_foreach(sb_comm* c, int op, int dtype, const void* const* in, void* const* out, const size_t* n, size_t seg_len, int exclusive) {
+  if(!c || !out || !n || seg_len == 0) return SB_ERR_BAD_ARG;
+  if(op != SB_OP_SEGREDUCE && op != SB_OP_SEGSCAN && op != SB_OP_SCAN) return SB_ERR_BAD_ARG;
+  if(op != SB_OP_SEGREDUCE && (!in || dtype_size(dtype) == 0)) return SB_ERR_BAD_ARG;
+  for(int r = 0; r < c->n; ++r)
+    if(n[r] % seg_len != 0) return SB_ERR_SEG_LEN;  // shards are cut on segment boundaries
+  if(int rc = comm_fork(c); rc != SB_OK) return rc;
+  for(int r = 0; r < c->n; ++r) {
+    sb_ctx* x = c->ctx[r];
+    int rc;
+    if(op == SB_OP_SEGREDUCE) {
+      switch(dtype) {
+      case SB_I16: rc = sb_segreduce_i16(x, (int16_t*)out[r], n[r], seg_len); break;
+      case SB_I32: rc = sb_segreduce_i32(x, (int32_t*)out[r], n[r], seg_len); break;
+      case SB_I64: rc = sb_segreduce_i64(x, (int64_t*)out[r], n[r], seg_len); break;
+      case SB_F32: rc = sb_segreduce_f32(x, (float*)out[r], n[r], seg_len); break;
+      case SB_F64: rc = sb_segreduce_f64(x, (double*)out[r], n[r], seg_len); break;
+      default: rc = SB_ERR_BAD_ARG;
+      }
+    } else if(op == SB_OP_SEGSCAN) {
+      switch(dtype) {
+      case SB_I32: rc = sb_segscan_i32(x, (const int32_t*)in[r], (int32_t*)out[r], n[r], seg_len, nullptr, exclusive); break;
+      case SB_I64: rc = sb_segscan_i64(x, (const int64_t*)in[r], (int64_t*)out[r], n[r], seg_len, nullptr, exclusive); break;
+      case SB_F32: rc = sb_segscan_f32(x, (const float*)in[r], (float*)out[r], n[r], seg_len, nullptr, exclusive); break;
+      default: rc = sb_segscan_f64(x, (const double*)in[r], (double*)out[r], n[r], seg_len, nullptr, exclusive); break;
+      }
+    } else {
+      switch(dtype) {
+      case SB_I32: rc = sb_scan_i32(x, (const int32_t*)in[r], (int32_t*)out[r], n[r], exclusive, seg_len, nullptr); break;
+      case SB_I64: rc = sb_scan_i64(x, (const int64_t*)in[r], (int64_t*)out[r], n[r], exclusive, seg_len, nullptr); break;
+      case SB_F32: rc = sb_scan_f32(x, (const float*)in[r], (float*)out[r], n[r], exclusive, seg_len, nullptr); break;
+      default: rc = sb_scan_f64(x, (const double*)in[r], (double*)out[r], n[r], exclusive, seg_len, nullptr); break;
+      }
+    }
+    if(rc != SB_OK) return comm_fail(c, rc);
   }
   return sb_comm_join(c);
 }

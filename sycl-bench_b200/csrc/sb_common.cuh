@@ -12,6 +12,8 @@
 
 #define SB_FULL_MASK 0xffffffffu
 
+struct sb_peer;
+
 struct sb_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -33,6 +35,12 @@ struct sb_ctx {
   unsigned long long* scan_ticket = nullptr;  // monotonically increasing, never reset
   unsigned long long scan_ticket_base = 0;    // host mirror of the value the next launch starts at
   uint32_t scan_epoch = 0;                    // descriptor generation, bumped per launch
+
+  // sb_scan_cyclic on one GPU: a private peer group of world size 1 (created on first use)
+  sb_peer* self_peer = nullptr;
+  // device-side error flag (pinned, mapped host memory): a kernel that gave up waiting for another CTA / GPU sets it
+  unsigned* err_host = nullptr;
+  unsigned* err_dev = nullptr;
 
   // timing
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -189,4 +197,6 @@ inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintp
 int sb_ctx_reserve_desc(sb_ctx* ctx, size_t count64, size_t count128);
 int sb_ctx_reserve_stage(sb_ctx* ctx, int which, size_t bytes);
 int sb_ctx_reserve_partials(sb_ctx* ctx, size_t slots);
-size_t sb_scan_tile_bytes();  // sb_scan.cu
+size_t sb_scan_min_tile_bytes();                      // sb_scan.cu: smallest tile any scan kernel uses (most descriptors)
+void sb_ctx_release_self_peer(sb_ctx* ctx);           // sb_scan_cyclic.cu
+int sb_ctx_take_error(sb_ctx* ctx);                   // sb_ctx.cu: SB_ERR_TIMEOUT once if a kernel raised the error flag

@@ -21,6 +21,8 @@ const char* sb_strerror(int status) {
   case SB_ERR_UNSUPPORTED: return "sb: device is not compute capability 10.x (library is sm_100a only)";
   case SB_ERR_TIMER: return "sb: sb_timer_end without sb_timer_begin";
   case SB_ERR_NCCL: return "sb: NCCL unavailable (libnccl.so.2 not loadable) or an NCCL call failed";
+  case SB_ERR_TIMEOUT: return "sb: a kernel gave up waiting for another CTA or GPU (results of that call are invalid)";
+  case SB_ERR_PEER: return "sb: peer memory unavailable (CUDA IPC / peer access failed, or a peer is not connected)";
   default: break;
   }
   if(status > 0) return cudaGetErrorString((cudaError_t)status);
@@ -73,6 +75,11 @@ int sb_ctx_create(int device, void* stream, sb_ctx** out) {
   if(e == cudaSuccess) e = cudaMalloc(&ctx->stage_small, 256);
   if(e == cudaSuccess) e = cudaMemset(ctx->reduce_ticket, 0, 256);
   if(e == cudaSuccess) e = cudaMemset(ctx->scan_ticket, 0, 256);
+  if(e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->err_host, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+  if(e == cudaSuccess) {
+    *ctx->err_host = 0u;
+    e = cudaHostGetDevicePointer((void**)&ctx->err_dev, ctx->err_host, 0);
+  }
   if(e == cudaSuccess) e = cudaEventCreate(&ctx->ev_begin);
   if(e == cudaSuccess) e = cudaEventCreate(&ctx->ev_end);
   if(e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -88,6 +95,8 @@ int sb_ctx_destroy(sb_ctx* ctx) {
   if(!ctx) return SB_OK;
   sb_device_guard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  sb_ctx_release_self_peer(ctx);
+  if(ctx->err_host) cudaFreeHost(ctx->err_host);
   cudaFree(ctx->partials);
   cudaFree(ctx->reduce_ticket);
   cudaFree(ctx->scan_ticket);
@@ -113,8 +122,9 @@ int sb_ctx_destroy(sb_ctx* ctx) {
 int sb_ctx_set_stream(sb_ctx* ctx, void* stream) {
   if(!ctx) return SB_ERR_BAD_ARG;
   sb_device_guard guard(ctx->device);
+  // tickets, partials and descriptors of the ctx may still be in use on the old stream, owned or borrowed
+  SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if(ctx->own_stream && ctx->stream) {
-    cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
     ctx->own_stream = false;
   }
@@ -133,7 +143,7 @@ int sb_ctx_sync(sb_ctx* ctx) {
   if(!ctx) return SB_ERR_BAD_ARG;
   sb_device_guard guard(ctx->device);
   SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  return SB_OK;
+  return sb_ctx_take_error(ctx);
 }
 
 int sb_ctx_device_name(sb_ctx* ctx, char* buf, size_t buflen) {
@@ -175,7 +185,7 @@ int sb_timer_end(sb_ctx* ctx, float* elapsed_ms) {
   SB_CUDA_TRY(cudaEventSynchronize(ctx->ev_end));
   SB_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, ctx->ev_begin, ctx->ev_end));
   ctx->timing = false;
-  return SB_OK;
+  return sb_ctx_take_error(ctx);
 }
 
 int sb_malloc(sb_ctx* ctx, void** dptr, size_t bytes) {
@@ -232,6 +242,14 @@ int sb_memset(sb_ctx* ctx, void* dst, int byte, size_t bytes) {
 }
 
 }  // extern "C"
+
+int sb_ctx_take_error(sb_ctx* ctx) {
+  if(ctx->err_host && *(volatile unsigned*)ctx->err_host) {
+    *(volatile unsigned*)ctx->err_host = 0u;
+    return SB_ERR_TIMEOUT;
+  }
+  return SB_OK;
+}
 
 // ---- workspace growth (amortised; never shrinks) -------------------------------------------------
 

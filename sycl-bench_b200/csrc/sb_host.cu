@@ -44,7 +44,16 @@ int download_chunk(sb_ctx* ctx, int k, void* h_dst, const void* d_src, size_t by
 int finish(sb_ctx* ctx) {
   SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if(ctx->d2h_stream) SB_CUDA_TRY(cudaStreamSynchronize(ctx->d2h_stream));
-  return SB_OK;
+  return sb_ctx_take_error(ctx);
+}
+
+// error exit of a chunked call: copies already queued still write into the caller's host buffer, so drain both
+// streams before handing the buffer back
+int fail(sb_ctx* ctx, int rc) {
+  cudaStreamSynchronize(ctx->stream);
+  if(ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+  (void)cudaGetLastError();
+  return rc;
 }
 
 template <typename A>
@@ -122,10 +131,9 @@ int sb_host_reduce(sb_ctx* ctx, int dtype, const void* h_in, size_t n, void* h_o
   case SB_F32: rc = sb_reduce_f32(ctx, (const float*)d_in, n, (float*)d_out); break;
   default: rc = sb_reduce_f64(ctx, (const double*)d_in, n, (double*)d_out); break;
   }
-  if(rc != SB_OK) return rc;
+  if(rc != SB_OK) return fail(ctx, rc);
   SB_CUDA_TRY(cudaMemcpyAsync(h_out, d_out, s, cudaMemcpyDeviceToHost, ctx->stream));
-  SB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  return SB_OK;
+  return finish(ctx);
 }
 
 int sb_host_scan(sb_ctx* ctx, int dtype, const void* h_in, void* h_out, size_t n, int exclusive, size_t group_len) {
@@ -151,10 +159,10 @@ int sb_host_scan(sb_ctx* ctx, int dtype, const void* h_in, void* h_out, size_t n
     if(k >= sb_ctx::kChunkEvents) SB_CUDA_TRY(cudaEventSynchronize(ctx->chunk_ev[k % sb_ctx::kChunkEvents]));
     SB_CUDA_TRY(cudaMemcpyAsync(d_in + b * s, hi + b * s, m * s, cudaMemcpyHostToDevice, ctx->stream));
     rc = scan_call(ctx, dtype, d_in + b * s, d_out + b * s, m, exclusive, global ? 0 : group_len, (global && k > 0) ? seed : nullptr);
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return fail(ctx, rc);
     if(global && b + m < n) launch_next_seed(ctx, dtype, d_in + (b + m - 1) * s, d_out + (b + m - 1) * s, exclusive, seed);
     rc = download_chunk(ctx, k, ho + b * s, d_out + b * s, m * s);
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return fail(ctx, rc);
   }
   return finish(ctx);
 }
@@ -178,10 +186,10 @@ int sb_host_segreduce(sb_ctx* ctx, int dtype, void* h_inout, size_t n, size_t se
     if(k >= sb_ctx::kChunkEvents) SB_CUDA_TRY(cudaEventSynchronize(ctx->chunk_ev[k % sb_ctx::kChunkEvents]));
     SB_CUDA_TRY(cudaMemcpyAsync(d + b * s, h + b * s, m * s, cudaMemcpyHostToDevice, ctx->stream));
     rc = segreduce_call(ctx, dtype, d + b * s, m, seg_len);
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return fail(ctx, rc);
     // only the heads changed, but the reference reads the whole buffer back (verify(), :102)
     rc = download_chunk(ctx, k, h + b * s, d + b * s, m * s);
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return fail(ctx, rc);
   }
   return finish(ctx);
 }
@@ -209,7 +217,7 @@ int sb_host_segscan(sb_ctx* ctx, int dtype, const void* h_in, void* h_out, size_
     }
     SB_CUDA_TRY(cudaMemcpyAsync(d, h_in, n * s, cudaMemcpyHostToDevice, ctx->stream));
     rc = segscan_call(ctx, dtype, d, d, n, seg_len, d_flags, exclusive);
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return fail(ctx, rc);
     SB_CUDA_TRY(cudaMemcpyAsync(h_out, d, n * s, cudaMemcpyDeviceToHost, ctx->stream));
     return finish(ctx);
   }
@@ -221,27 +229,38 @@ int sb_host_segscan(sb_ctx* ctx, int dtype, const void* h_in, void* h_out, size_
     if(k >= sb_ctx::kChunkEvents) SB_CUDA_TRY(cudaEventSynchronize(ctx->chunk_ev[k % sb_ctx::kChunkEvents]));
     SB_CUDA_TRY(cudaMemcpyAsync(d + b * s, hi + b * s, m * s, cudaMemcpyHostToDevice, ctx->stream));
     rc = segscan_call(ctx, dtype, d + b * s, d + b * s, m, seg_len, nullptr, exclusive);
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return fail(ctx, rc);
     rc = download_chunk(ctx, k, ho + b * s, d + b * s, m * s);
-    if(rc != SB_OK) return rc;
+    if(rc != SB_OK) return fail(ctx, rc);
   }
   return finish(ctx);
+}
+
+// descriptors an op on n elements needs at most: the smallest tile any scan kernel uses gives the largest count
+static size_t scan_desc_upper_bound(size_t n, size_t s) {
+  const size_t tile = sb_scan_min_tile_bytes() / s;
+  return 2 * ((n + tile - 1) / tile) + 64;  // tile descriptors + one prefix per round + slack
 }
 
 size_t sb_workspace_bytes(int op, int dtype, size_t n) {
   const size_t s = dtype_size(dtype);
   if(s == 0) return 0;
   switch(op) {
-  case SB_OP_REDUCE: return 148 * 32 * 8 + 256;  // block partials + ticket
+  case SB_OP_REDUCE: return 256 * 32 * 8 + 256;  // block partials for up to 256 SMs + tickets
   case SB_OP_SCAN:
-  case SB_OP_SEGSCAN: {
-    const size_t tile = sb_scan_tile_bytes() / s;
-    const size_t tiles = (n + tile - 1) / tile;
-    return (2 * tiles + 64) * (s == 4 ? 8 : 16) + 256;  // tile descriptors + per-round prefixes + ticket
-  }
+  case SB_OP_SEGSCAN: return scan_desc_upper_bound(n, s) * (s == 4 ? 8 : 16) + 256;
   case SB_OP_SEGREDUCE: return 0;
   default: return 0;
   }
+}
+
+int sb_ctx_reserve(sb_ctx* ctx, int op, int dtype, size_t n) {
+  const size_t s = dtype_size(dtype);
+  if(!ctx || s == 0) return SB_ERR_BAD_ARG;
+  if(op != SB_OP_SCAN && op != SB_OP_SEGSCAN) return SB_OK;  // everything else uses the fixed-size scratch of sb_ctx_create
+  sb_device_guard guard(ctx->device);
+  const size_t count = scan_desc_upper_bound(n, s);
+  return sb_ctx_reserve_desc(ctx, s == 4 ? count : 0, s == 8 ? count : 0);
 }
 
 }  // extern "C"

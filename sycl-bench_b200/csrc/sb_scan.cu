@@ -42,12 +42,10 @@
 //  carries a per-launch epoch, so descriptors are never reset between launches.  Segmented
 //  variants run the same code on (value, head-flag) pairs: (v1,f1)(+)(v2,f2) = (f2 ? v2 : v1+v2,
 //  f1|f2); if every tile starts on a head (power-of-two segment <= tile) no descriptor is touched.
-#include <cuda.h>
-
 #include <atomic>
 #include <cstdlib>
 
-#include "sb_common.cuh"
+#include "sb_scan_tile.cuh"
 
 namespace {
 
@@ -94,61 +92,7 @@ constexpr int WS_NW_NARROW = SB_WS_NW_NARROW;
 constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
 constexpr int WS_NSLOT = 2 * WS_DEPTH + 2;  // a fast warp is at most DEPTH+1 tiles ahead of a slow one
 
-enum : uint32_t { ST_AGG = 1u, ST_INCL = 2u };
-enum { MODE_PLAIN = 0, MODE_IMPLICIT = 1, MODE_FLAGS = 2 };
-
-template <typename A, int NW_, int K> struct TileCfg {
-  static constexpr int VEC = 16 / sizeof(A);
-  static constexpr int NW = NW_;
-  static constexpr int ROW = 32 * VEC;      // elements one warp covers with one 128-bit access per lane
-  static constexpr int WCHUNK = K * ROW;    // consecutive elements owned by a warp
-  static constexpr int TILE = NW * WCHUNK;  // elements per tile
-  static constexpr int TILE_BYTES = NW * K * 512;
-};
-
-// ---- descriptors ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t bits_of(uint32_t v) { return v; }
-__device__ __forceinline__ uint32_t bits_of(float v) { return __float_as_uint(v); }
-__device__ __forceinline__ unsigned long long bits_of(unsigned long long v) { return v; }
-__device__ __forceinline__ unsigned long long bits_of(double v) { return (unsigned long long)__double_as_longlong(v); }
-template <typename A> __device__ __forceinline__ A from_bits32(uint32_t b);
-template <> __device__ __forceinline__ uint32_t from_bits32<uint32_t>(uint32_t b) { return b; }
-template <> __device__ __forceinline__ float from_bits32<float>(uint32_t b) { return __uint_as_float(b); }
-template <typename A> __device__ __forceinline__ A from_bits64(unsigned long long b);
-template <> __device__ __forceinline__ unsigned long long from_bits64<unsigned long long>(unsigned long long b) { return b; }
-template <> __device__ __forceinline__ double from_bits64<double>(unsigned long long b) { return __longlong_as_double((long long)b); }
-
-template <typename A, int BYTES = sizeof(A)> struct Desc;
-
-template <typename A> struct Desc<A, 4> {
-  using word = unsigned long long;
-  static __device__ __forceinline__ void store(word* d, uint32_t status, A v) {
-    const word w = ((word)bits_of(v) << 32) | status;
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(d), "l"(w) : "memory");
-  }
-  static __device__ __forceinline__ void load(const word* d, uint32_t& status, A& v) {
-    word w;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(d) : "memory");
-    status = (uint32_t)w;
-    v = from_bits32<A>((uint32_t)(w >> 32));
-  }
-};
-
-struct alignas(16) desc128_t { unsigned long long status, value; };
-
-template <typename A> struct Desc<A, 8> {
-  using word = desc128_t;
-  static __device__ __forceinline__ void store(word* d, uint32_t status, A v) {
-    const unsigned long long s = status, b = bits_of(v);
-    asm volatile("{.reg .b128 t; mov.b128 t, {%1,%2}; st.relaxed.gpu.global.b128 [%0], t;}" ::"l"(d), "l"(s), "l"(b) : "memory");
-  }
-  static __device__ __forceinline__ void load(const word* d, uint32_t& status, A& v) {
-    unsigned long long s, b;
-    asm volatile("{.reg .b128 t; ld.relaxed.gpu.global.b128 t, [%2]; mov.b128 {%0,%1}, t;}" : "=l"(s), "=l"(b) : "l"(d) : "memory");
-    status = (s >> 32) ? 0u : (uint32_t)s;
-    v = from_bits64<A>(b);
-  }
-};
+using namespace sbscan;
 
 // classic decoupled look-back by one full warp: sum the aggregates of the predecessors down to the
 // first tile whose inclusive prefix is known (ticketed kernel)
@@ -254,349 +198,6 @@ __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, 
   return total;
 }
 
-// ---- mbarrier / TMA bulk-copy primitives ------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  while(!done) {
-    asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-// ---- per-warp building blocks ---------------------------------------------------------------------------------
-// head flags of the K x VEC elements a thread owns (bit c of hf[j] = element c of row j is a head)
-template <typename A, int MODE, int K>
-__device__ __forceinline__ void tile_head_flags(unsigned (&hf)[K], size_t wbase, size_t n, size_t seg_len, size_t seg_mask,
-    const uint8_t* __restrict__ flags) {
-  constexpr int VEC = 16 / sizeof(A);
-  constexpr int ROW = 32 * VEC;
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    const size_t idx = wbase + (size_t)j * ROW;
-    hf[j] = 0;
-    if(MODE == MODE_IMPLICIT) {
-      if(seg_mask != ~(size_t)0) {
-        if(seg_mask >= (size_t)(VEC - 1)) {
-          // power-of-two segment of at least one vector: only element 0 of an aligned vector can be a head
-          hf[j] = (idx & seg_mask) == 0 ? 1u : 0u;
-        } else {
-#pragma unroll
-          for(int c = 0; c < VEC; ++c) hf[j] |= (((idx + c) & seg_mask) == 0 ? 1u : 0u) << c;
-        }
-      } else {
-        size_t r = idx % seg_len;
-#pragma unroll
-        for(int c = 0; c < VEC; ++c) {
-          hf[j] |= (r == 0 ? 1u : 0u) << c;
-          r = (r + 1 == seg_len) ? 0 : r + 1;
-        }
-      }
-    } else if(MODE == MODE_FLAGS) {
-      if(idx + VEC <= n && (reinterpret_cast<uintptr_t>(flags + idx) & (VEC - 1)) == 0) {
-        uint32_t w;  // VEC flag bytes in one access
-        if(VEC == 4) w = __ldg(reinterpret_cast<const uint32_t*>(flags + idx));
-        else w = __ldg(reinterpret_cast<const uint16_t*>(flags + idx));
-#pragma unroll
-        for(int c = 0; c < VEC; ++c) hf[j] |= (((w >> (8 * c)) & 0xffu) ? 1u : 0u) << c;
-      } else {
-#pragma unroll
-        for(int c = 0; c < VEC; ++c) hf[j] |= ((idx + c < n && flags[idx + c]) ? 1u : 0u) << c;
-      }
-      if(idx == 0) hf[j] |= 1u;
-    }
-  }
-}
-
-// explicit head flags staged in the ring by the producer (one flag byte per element, warp chunk at `wflags`):
-// VEC bytes per lane and row, bank-conflict free
-template <typename A, int K>
-__device__ __forceinline__ void tile_head_flags_ring(unsigned (&hf)[K], const unsigned char* wflags, size_t wbase) {
-  constexpr int VEC = 16 / sizeof(A);
-  constexpr int ROW = 32 * VEC;
-  const unsigned char* fp = wflags + (threadIdx.x & 31) * VEC;
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    uint32_t w;
-    if(VEC == 4) w = *reinterpret_cast<const uint32_t*>(fp + j * ROW);
-    else w = *reinterpret_cast<const uint16_t*>(fp + j * ROW);
-    hf[j] = 0;
-#pragma unroll
-    for(int c = 0; c < VEC; ++c) hf[j] |= (((w >> (8 * c)) & 0xffu) ? 1u : 0u) << c;
-    if(wbase + (size_t)j * ROW == 0) hf[j] |= 1u;  // element 0 always starts a segment
-  }
-}
-
-// guarded global -> register load of a (possibly partial, possibly unaligned) tile
-template <typename A, bool ALIGNED, int K>
-__device__ __forceinline__ void tile_load_global(A (&v)[K][16 / sizeof(A)], const A* in, size_t wbase, bool full_tile, size_t n) {
-  constexpr int VEC = 16 / sizeof(A);
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    const size_t idx = wbase + (size_t)j * (32 * VEC);
-    if(ALIGNED && (full_tile || idx + VEC <= n)) {
-      sb::Vec<A> t = sb::ldg_stream<A>(in + idx);
-#pragma unroll
-      for(int c = 0; c < VEC; ++c) v[j][c] = t.v[c];
-    } else {
-#pragma unroll
-      for(int c = 0; c < VEC; ++c) v[j][c] = (idx + c < n) ? in[idx + c] : A(0);
-    }
-  }
-}
-
-// shared-memory ring -> registers (the lane-consecutive 16-byte layout is bank-conflict free)
-template <typename A, int K>
-__device__ __forceinline__ void tile_load_smem(A (&v)[K][16 / sizeof(A)], const unsigned char* warp_rows) {
-  constexpr int VEC = 16 / sizeof(A);
-  const unsigned char* sp = warp_rows + (threadIdx.x & 31) * 16;
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    const sb::Vec<A> t = *reinterpret_cast<const sb::Vec<A>*>(sp + (size_t)j * 512);
-#pragma unroll
-    for(int c = 0; c < VEC; ++c) v[j][c] = t.v[c];
-  }
-}
-
-// the warp's K rows reduced to (sum since the last head, contains a head)
-template <typename A, int MODE, int K>
-__device__ __forceinline__ void warp_reduce_rows(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A& agg, bool& has_head) {
-  constexpr int VEC = 16 / sizeof(A);
-  const int lane = threadIdx.x & 31;
-  if(MODE == MODE_PLAIN) {
-    A s = A(0);
-#pragma unroll
-    for(int j = 0; j < K; ++j) {
-      A r = v[j][0];
-#pragma unroll
-      for(int c = 1; c < VEC; ++c) r += v[j][c];
-      s += r;
-    }
-    agg = sb::warp_sum<A>(s);
-    has_head = false;
-    return;
-  }
-  {
-    unsigned any = 0;
-#pragma unroll
-    for(int j = 0; j < K; ++j) any |= hf[j];
-    if(!__any_sync(SB_FULL_MASK, any != 0u)) {  // no head in the warp chunk: one warp sum instead of K
-      warp_reduce_rows<A, MODE_PLAIN, K>(v, hf, agg, has_head);
-      return;
-    }
-  }
-  A run = A(0);
-  bool runf = false;
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    A s = A(0);
-    bool f = false;
-#pragma unroll
-    for(int c = 0; c < VEC; ++c) {
-      if((hf[j] >> c) & 1u) {
-        s = v[j][c];
-        f = true;
-      } else {
-        s += v[j][c];
-      }
-    }
-    const unsigned hm = __ballot_sync(SB_FULL_MASK, f);
-    if(hm) {
-      const int hl = 31 - __clz(hm);
-      run = sb::warp_sum<A>(lane >= hl ? s : A(0));
-      runf = true;
-    } else {
-      run += sb::warp_sum<A>(s);
-    }
-  }
-  agg = run;
-  has_head = runf;
-}
-
-// pass 1: thread partials -> per-row warp segmented scan.  The K row scans are independent shuffle
-// chains (the compiler interleaves them: ILP K); the carries between rows are added afterwards.
-// carry_in[j] = running sum entering the thread's part of row j, relative to the start of the warp
-// chunk (or the last head inside it); open[j] = no head between the start of the chunk and there.
-// Segmented variant of pass 1 with the row scans chained through the carry: fewer live registers
-// (no per-row totals / head masks), which matters more than ILP once head flags are in play.
-template <typename A, int MODE, int K>
-__device__ __forceinline__ void tile_pass1_chained(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A (&carry_in)[K],
-    bool (&open)[K], A& warp_agg, bool& warp_has_head) {
-  constexpr int VEC = 16 / sizeof(A);
-  const int lane = threadIdx.x & 31;
-  A row_carry = A(0);
-  bool warp_open = true;
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    A s = A(0);
-    bool f = false;
-#pragma unroll
-    for(int c = 0; c < VEC; ++c) {
-      if((hf[j] >> c) & 1u) {
-        s = v[j][c];
-        f = true;
-      } else {
-        s += v[j][c];
-      }
-    }
-    const unsigned hm = __ballot_sync(SB_FULL_MASK, f);
-    const unsigned m = hm & (0xffffffffu >> (31 - lane));
-    const int h = m ? 31 - __clz(m) : 0;
-    if(lane == 0 && !f) s += row_carry;
-    A inc = s;
-#pragma unroll
-    for(int d = 1; d < 32; d <<= 1) {
-      const A t = sb::shfl_up(inc, d);
-      if(lane >= h + d) inc += t;
-    }
-    A ex = sb::shfl_up(inc, 1);
-    if(lane == 0) ex = row_carry;
-    carry_in[j] = ex;
-    open[j] = warp_open && (hm & ((1u << lane) - 1u)) == 0u;
-    row_carry = sb::shfl_idx(inc, 31);
-    if(hm) warp_open = false;
-  }
-  warp_agg = row_carry;
-  warp_has_head = !warp_open;
-}
-
-template <typename A, int MODE, int K>
-__device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A (&carry_in)[K], bool (&open)[K],
-    A& warp_agg, bool& warp_has_head) {
-  if(MODE != MODE_PLAIN) {
-    // a warp chunk without any head (the common case once segments are longer than K rows) is a plain scan:
-    // take the unchained path, whose K row scans are independent shuffle chains
-    unsigned any = 0;
-#pragma unroll
-    for(int j = 0; j < K; ++j) any |= hf[j];
-    if(!__any_sync(SB_FULL_MASK, any != 0u)) {
-      tile_pass1<A, MODE_PLAIN, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
-      return;
-    }
-    tile_pass1_chained<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
-    return;
-  }
-  constexpr int VEC = 16 / sizeof(A);
-  const int lane = threadIdx.x & 31;
-  A tot[K];          // row sum since the last head of the row (whole row if it has none)
-  unsigned hm[K];    // lanes of row j that contain a head
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    A s = A(0);
-    bool f = false;
-#pragma unroll
-    for(int c = 0; c < VEC; ++c) {
-      if(MODE != MODE_PLAIN && ((hf[j] >> c) & 1u)) {
-        s = v[j][c];
-        f = true;
-      } else {
-        s += v[j][c];
-      }
-    }
-    hm[j] = 0;
-    int h = 0;
-    if(MODE != MODE_PLAIN) {
-      hm[j] = __ballot_sync(SB_FULL_MASK, f);
-      const unsigned m = hm[j] & (0xffffffffu >> (31 - lane));
-      h = m ? 31 - __clz(m) : 0;
-    }
-    A inc = s;
-    if(MODE == MODE_PLAIN) {
-      sb::warp_inclusive_scan<A>(inc);  // predicated shuffle-adds
-    } else {
-#pragma unroll
-      for(int d = 1; d < 32; d <<= 1) {
-        const A t = sb::shfl_up(inc, d);
-        if(lane >= h + d) inc += t;
-      }
-    }
-    const A ex = sb::shfl_up(inc, 1);
-    carry_in[j] = lane == 0 ? A(0) : ex;
-    tot[j] = sb::shfl_idx(inc, 31);
-  }
-  A off = A(0);
-  bool warp_open = true;
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    const bool row_open = MODE == MODE_PLAIN || (hm[j] & ((1u << lane) - 1u)) == 0u;  // no head in front of me in this row
-    if(row_open) carry_in[j] += off;
-    open[j] = warp_open && row_open;
-    if(MODE != MODE_PLAIN && hm[j]) {
-      off = tot[j];
-      warp_open = false;
-    } else {
-      off += tot[j];
-    }
-  }
-  warp_agg = off;
-  warp_has_head = !warp_open;
-}
-
-// pass 2: rescan with the known carry, 128-bit coalesced stores from registers
-template <typename A, int MODE, bool ALIGNED, int K>
-__device__ __forceinline__ void tile_pass2_store(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], const A (&carry_in)[K],
-    const bool (&open)[K], A warp_prefix, size_t wbase, bool full_tile, size_t n, A* out, int exclusive) {
-  constexpr int VEC = 16 / sizeof(A);
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    const size_t idx = wbase + (size_t)j * (32 * VEC);
-    A r = carry_in[j] + (open[j] ? warp_prefix : A(0));
-    sb::Vec<A> o;
-#pragma unroll
-    for(int c = 0; c < VEC; ++c) {
-      if(MODE != MODE_PLAIN && ((hf[j] >> c) & 1u)) r = A(0);
-      const A e = r;
-      r += v[j][c];
-      o.v[c] = exclusive ? e : r;
-    }
-    if(ALIGNED && (full_tile || idx + VEC <= n)) {
-      sb::stg_vec<A>(out + idx, o);
-    } else {
-#pragma unroll
-      for(int c = 0; c < VEC; ++c)
-        if(idx + c < n) out[idx + c] = o.v[c];
-    }
-  }
-}
-
-// prefix of the warps in front of `warp` inside a tile and the tile's own (aggregate, has-head)
-template <typename A, int MODE, int NW>
-__device__ __forceinline__ void combine_warps(const A* wagg, const int* wflag, int warp, A& my_prefix, bool& my_open, A& tile_agg,
-    bool& tile_has_head) {
-  A run = A(0);
-  bool run_open = true;
-  my_prefix = A(0);
-  my_open = true;
-#pragma unroll
-  for(int u = 0; u < NW; ++u) {
-    if(u == warp) {
-      my_prefix = run;
-      my_open = run_open;
-    }
-    if(MODE != MODE_PLAIN && wflag[u]) {
-      run = wagg[u];
-      run_open = false;
-    } else {
-      run += wagg[u];
-    }
-  }
-  tile_agg = run;
-  tile_has_head = !run_open;
-}
-
 // ---- kernel 1: one CTA per tile, tile id from an atomic ticket (unaligned buffers, small inputs) -------------
 template <typename A, int MODE, bool ALIGNED>
 __global__ void __launch_bounds__(SCAN_NT)
@@ -665,56 +266,6 @@ scan_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t
   }
   const A warp_prefix = my_prefix + (my_open ? tile_prefix : A(0));
   tile_pass2_store<A, MODE, ALIGNED, K>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, exclusive);
-}
-
-// Round look-back with every descriptor load of the round in flight at once (G <= 32 * MAXB): one L2 round
-// trip when the aggregates are there, instead of one per SCAN_WINDOW x 32 descriptors.  The phase trace
-// (profiles/tb_trace.py) showed 2-4.5 us per look-back with the windowed walk — several dependent L2 round
-// trips at ~1 us each under streaming load — which capped the kernel at one tile per ~3.4 us and CTA.
-template <typename A, int MAXB>
-__device__ __forceinline__ A lookback_round_wide(const typename Desc<A>::word* desc, const typename Desc<A>::word* rdesc, long long tile,
-    long long G, uint32_t epoch, const A* __restrict__ seed) {
-  const int lane = sb::lane_id();
-  const long long r = tile / G;
-  const int pos = (int)(tile - r * G);
-  const typename Desc<A>::word* row = desc + r * G;
-  uint32_t rst = (epoch << 2) | ST_INCL;
-  A rval = A(0);
-  if(lane == 0) {
-    if(r > 0) Desc<A>::load(rdesc + (r - 1), rst, rval);
-    else if(seed) rval = *seed;
-  }
-  uint32_t st[MAXB];
-  A val[MAXB];
-#pragma unroll
-  for(int u = 0; u < MAXB; ++u) {
-    const int q = u * 32 + lane;
-    st[u] = (epoch << 2) | ST_AGG;
-    val[u] = A(0);
-    if(q < pos) Desc<A>::load(row + q, st[u], val[u]);
-  }
-  // one L2 round trip per polling pass: every missing descriptor (and the round prefix) is re-requested at once
-  for(;;) {
-    bool missing = false;
-#pragma unroll
-    for(int u = 0; u < MAXB; ++u) {
-      const int q = u * 32 + lane;
-      if(q < pos && (st[u] >> 2) != epoch) {
-        missing = true;
-        Desc<A>::load(row + q, st[u], val[u]);
-      }
-    }
-    if(lane == 0 && r > 0 && (rst >> 2) != epoch) {
-      missing = true;
-      Desc<A>::load(rdesc + (r - 1), rst, rval);
-    }
-    if(!__any_sync(SB_FULL_MASK, missing)) break;
-  }
-  A lane_sum = A(0);
-#pragma unroll
-  for(int u = 0; u < MAXB; ++u) lane_sum += val[u];
-  const A total = sb::warp_sum<A>(lane_sum);
-  return total + sb::shfl_idx(rval, 0);
 }
 
 // ---- kernel 2: persistent, warp-specialised, TMA ring (see header) ---------------------------------------------
@@ -1011,249 +562,6 @@ scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg
   }
 }
 
-// ---- kernel 4: thread-blocked scan through swizzled TMA tensor tiles (global scans, 16-byte aligned) --------
-// The array is viewed as a 2-D tensor of 128-byte rows.  A tile is TB_NW*32 rows; TMA (cp.async.bulk.tensor,
-// SWIZZLE_128B) drops it into the ring so that chunk j of row r sits at chunk j ^ (r & 7): every worker thread
-// owns ONE row = 128 consecutive bytes of the array and reads / rewrites it with eight conflict-free
-// LDS.128 / STS.128.  Per tile a thread does one serial scan of its 32 (16) elements, ONE warp scan of the
-// thread totals and one add per element — about 6x fewer instructions than the row-per-warp kernels above
-// (ncu: 51 warp instructions per 64-bit element there, issue slots 50 % busy).  Results are written back into
-// the same ring stage and leave through a TMA tensor store issued by a dedicated warp, so worker warps issue
-// no global memory instruction at all.  Rows beyond the end of the array are zero-filled on load and clipped
-// on store by the TMA unit: no ragged-tile code.  Warp roles: TB_NW workers, loader, storer, two look-back warps (even / odd tiles of the CTA).
-#ifndef SB_TB_NW
-#define SB_TB_NW 12
-#endif
-#ifndef SB_TB_STAGES
-#define SB_TB_STAGES 3
-#endif
-constexpr int TB_NW = SB_TB_NW, TB_STAGES = SB_TB_STAGES;
-constexpr int TB_ROWS = TB_NW * 32;          // rows (= worker threads) per tile
-constexpr int TB_STAGE_BYTES = TB_ROWS * 128;
-constexpr int TB_BOXES = (TB_ROWS + 255) / 256;  // TMA boxes per tile (box height is limited to 256 rows)
-constexpr int TB_BOX_ROWS = TB_ROWS / TB_BOXES;
-static_assert(TB_BOX_ROWS * TB_BOXES == TB_ROWS && (TB_BOX_ROWS * 128) % 1024 == 0, "tile does not split into swizzle-aligned boxes");
-constexpr int TB_THREADS = (TB_NW + 4) * 32;  // workers, loader, storer, two look-back warps
-
-// optional phase trace (-DSB_TB_TRACE): %globaltimer stamps of the first TB_TRACE_TILES tiles of every CTA
-#ifdef SB_TB_TRACE
-constexpr int TB_TRACE_TILES = 48, TB_TRACE_EVENTS = 16;
-__device__ unsigned long long tb_trace[160][TB_TRACE_TILES][TB_TRACE_EVENTS];
-__device__ __forceinline__ void tb_stamp(long long tile_i, int ev) {
-  if(tile_i < TB_TRACE_TILES && blockIdx.x < 160) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    tb_trace[blockIdx.x][tile_i][ev] = t;
-  }
-}
-#define TB_STAMP(i, ev) tb_stamp(i, ev)
-#else
-#define TB_STAMP(i, ev)
-#endif
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
-
-template <typename A>
-__global__ void __launch_bounds__(TB_THREADS, 1)
-scan_tb_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, long long total_rows, int exclusive,
-    const A* __restrict__ seed, typename Desc<A>::word* desc, typename Desc<A>::word* total_slot, uint32_t epoch, long long num_tiles) {
-  constexpr int E = 128 / sizeof(A);   // elements per row / thread
-  constexpr int VEC = 16 / sizeof(A);  // elements per 16-byte chunk
-  extern __shared__ unsigned char tb_raw[];
-  __shared__ __align__(8) unsigned long long full_bar[TB_STAGES], empty_bar[TB_STAGES], stored_bar, out_free_bar, agg_bar[2], prefix_bar[2];
-  __shared__ A s_wagg[2][TB_NW], s_wprefix[2][TB_NW];
-
-  const uint32_t ring = (smem_u32(tb_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024-byte aligned tiles
-  const uint32_t out_tile = ring + TB_STAGES * TB_STAGE_BYTES;  // staging tile of the TMA store
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long G = gridDim.x;
-  const long long my_tiles = (num_tiles - (long long)blockIdx.x + G - 1) / G;
-
-  if(threadIdx.x == 0) {
-#pragma unroll
-    for(int s = 0; s < TB_STAGES; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), TB_NW);
-    }
-    mbar_init(smem_u32(&stored_bar), TB_NW);
-    mbar_init(smem_u32(&out_free_bar), 1);
-#pragma unroll
-    for(int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&agg_bar[s]), TB_NW);
-      mbar_init(smem_u32(&prefix_bar[s]), TB_NW);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();  // the only block-wide barrier
-
-  if(warp == TB_NW) {
-    // ===== loader: TMA tensor loads into the ring; a stage is free again as soon as the workers hold it in registers =====
-    if(lane != 0) return;
-    for(long long i = 0; i < my_tiles; ++i) {
-      const int stage = (int)(i % TB_STAGES);
-      if(i >= TB_STAGES) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)((i / TB_STAGES) - 1) & 1u);
-      const long long row0 = ((long long)blockIdx.x + i * G) * TB_ROWS;
-      const uint32_t bar = smem_u32(&full_bar[stage]);
-      int boxes = 0;
-#pragma unroll
-      for(int h = 0; h < TB_BOXES; ++h) boxes += (row0 + h * TB_BOX_ROWS < total_rows) ? 1 : 0;
-      TB_STAMP(i, 0);  // load issue
-      mbar_expect_tx(bar, (uint32_t)boxes * TB_BOX_ROWS * 128u);
-#pragma unroll
-      for(int h = 0; h < TB_BOXES; ++h)
-        if(row0 + h * TB_BOX_ROWS < total_rows) tma_load_2d(ring + stage * TB_STAGE_BYTES + h * TB_BOX_ROWS * 128, &tm_in, 0, (int)(row0 + h * TB_BOX_ROWS), bar);
-    }
-  } else if(warp == TB_NW + 1 || warp == TB_NW + 3) {
-    // ===== look-back warps (one for the even, one for the odd tiles of this CTA, so that consecutive look-backs
-    // overlap): tile aggregate -> descriptor, round look-back, per-warp prefixes for the workers =====
-    const typename Desc<A>::word* rdesc = desc + num_tiles;
-    for(long long i = (warp == TB_NW + 1) ? 0 : 1; i < my_tiles; i += 2) {
-      const int slot = (int)(i & 1);
-      const long long tile = (long long)blockIdx.x + i * G;
-      mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(i >> 1) & 1u);
-      if(lane == 0) TB_STAMP(i, 1);  // aggregates of all warps in
-      const A mine = lane < TB_NW ? s_wagg[slot][lane] : A(0);
-      A incl = mine;
-#pragma unroll
-      for(int d = 1; d < 32; d <<= 1) {
-        const A up = sb::shfl_up(incl, d);
-        if(lane >= d) incl += up;
-      }
-      const A tile_agg = sb::shfl_idx(incl, 31);
-      if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | ST_AGG, tile_agg);
-      const A p = G <= 160 ? lookback_round_wide<A, 5>(desc, rdesc, tile, G, epoch, seed) : lookback_round<A, MODE_PLAIN>(desc, rdesc, tile, G, epoch, seed);
-      if(lane == 0 && (tile + 1) % G == 0)
-        Desc<A>::store(const_cast<typename Desc<A>::word*>(rdesc) + tile / G, (epoch << 2) | ST_INCL, p + tile_agg);
-      if(lane == 0 && tile == num_tiles - 1) Desc<A>::store(total_slot, (epoch << 2) | ST_INCL, p + tile_agg);  // for the tail kernel
-      if(lane == 0) TB_STAMP(i, 2);  // look-back done
-      if(lane < TB_NW) {  // every writer releases its own value: the barrier counts TB_NW arrivals
-        s_wprefix[slot][lane] = p + (incl - mine);
-        mbar_arrive(smem_u32(&prefix_bar[slot]));
-      }
-    }
-  } else if(warp == TB_NW + 2) {
-    // ===== storer: TMA tensor store of the staging tile =====
-    if(lane != 0) return;
-    for(long long i = 0; i < my_tiles; ++i) {
-      mbar_wait(smem_u32(&stored_bar), (uint32_t)i & 1u);
-      TB_STAMP(i, 3);  // all rows written to the staging tile
-      const long long row0 = ((long long)blockIdx.x + i * G) * TB_ROWS;
-#pragma unroll
-      for(int h = 0; h < TB_BOXES; ++h)
-        if(row0 + h * TB_BOX_ROWS < total_rows) tma_store_2d(&tm_out, out_tile + h * TB_BOX_ROWS * 128, 0, (int)(row0 + h * TB_BOX_ROWS));
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging tile has been read
-      TB_STAMP(i, 4);  // staging tile free
-      mbar_arrive(smem_u32(&out_free_bar));
-    }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores have landed before the CTA retires
-  } else {
-    // ===== workers: thread t owns row t of every tile.  Software pipeline over two register sets:
-    //   phase A(k+1): ring -> registers (the stage goes straight back to the loader), serial row scan, warp scan
-    //                 of the row totals, warp aggregate to the look-back warp
-    //   phase B(k)  : wait for the tile prefix (it has had a whole tile time to arrive), add, write the row to
-    //                 the staging tile, hand it to the storer.
-    const uint32_t row_off = (uint32_t)threadIdx.x * 128u;
-    const uint32_t sw = (uint32_t)(threadIdx.x & 7);
-    auto phase_a = [&](long long k, A (&x)[E], A& thread_excl) {
-      const int stage = (int)(k % TB_STAGES), slot = (int)(k & 1);
-      const uint32_t row = ring + stage * TB_STAGE_BYTES + row_off;
-      const bool valid = ((long long)blockIdx.x + k * G) * TB_ROWS + threadIdx.x < total_rows;
-      if(threadIdx.x == 0) TB_STAMP(k, 5);  // phase A: start waiting for the data
-      mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(k / TB_STAGES) & 1u);
-      if(threadIdx.x == 0) TB_STAMP(k, 6);  // data there
-#pragma unroll
-      for(int j = 0; j < 8; ++j) {
-        uint4 q;
-        const uint32_t addr = row + (((uint32_t)j ^ sw) << 4);
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr) : "memory");
-        const sb::Vec<A>& t = *reinterpret_cast<const sb::Vec<A>*>(&q);
-#pragma unroll
-        for(int c = 0; c < VEC; ++c) x[j * VEC + c] = valid ? t.v[c] : A(0);  // rows behind the end of the array count as zeros
-      }
-      // serial inclusive scan of the row (left to right: the order of a sequential scan)
-#pragma unroll
-      for(int e = 1; e < E; ++e) x[e] += x[e - 1];
-      __syncwarp();
-      if(lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));  // the warp's rows live in registers now
-      A incl = x[E - 1];
-#pragma unroll
-      for(int d = 1; d < 32; d <<= 1) {
-        const A up = sb::shfl_up(incl, d);
-        if(lane >= d) incl += up;
-      }
-      thread_excl = incl - x[E - 1];
-      __syncwarp();  // every lane is past its read of s_wprefix[slot] (phase B of tile k-2) before the slot is re-armed
-      if(lane == 31) {
-        s_wagg[slot][warp] = incl;
-        mbar_arrive(smem_u32(&agg_bar[slot]));
-      }
-      if(threadIdx.x == 0) TB_STAMP(k, 7);  // phase A done
-    };
-    auto phase_b = [&](long long k, A (&x)[E], A thread_excl) {
-      const int slot = (int)(k & 1);
-      if(threadIdx.x == 0) TB_STAMP(k, 8);  // phase B: waiting for the prefix
-      mbar_wait(smem_u32(&prefix_bar[slot]), (uint32_t)(k >> 1) & 1u);
-      if(threadIdx.x == 0) TB_STAMP(k, 9);  // prefix there
-      const A add = s_wprefix[slot][warp] + thread_excl;
-      if(exclusive) {
-#pragma unroll
-        for(int e = E - 1; e > 0; --e) x[e] = x[e - 1] + add;
-        x[0] = add;
-      } else {
-#pragma unroll
-        for(int e = 0; e < E; ++e) x[e] += add;
-      }
-      if(k > 0) mbar_wait(smem_u32(&out_free_bar), (uint32_t)(k - 1) & 1u);  // the store of tile k-1 has read the staging tile
-#pragma unroll
-      for(int j = 0; j < 8; ++j) {
-        sb::Vec<A> t;
-#pragma unroll
-        for(int c = 0; c < VEC; ++c) t.v[c] = x[j * VEC + c];
-        const uint32_t addr = out_tile + row_off + (((uint32_t)j ^ sw) << 4);
-        const uint4& q = *reinterpret_cast<const uint4*>(&t);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the rows visible to the TMA store
-      __syncwarp();
-      if(threadIdx.x == 0) TB_STAMP(k, 10);  // phase B done
-      if(lane == 0) mbar_arrive(smem_u32(&stored_bar));
-    };
-    A xa[E], xb[E];
-    A ea = A(0), eb = A(0);
-    if(my_tiles > 0) phase_a(0, xa, ea);
-    for(long long k = 0; k < my_tiles; k += 2) {
-      if(k + 1 < my_tiles) phase_a(k + 1, xb, eb);
-      phase_b(k, xa, ea);
-      if(k + 1 < my_tiles) {
-        if(k + 2 < my_tiles) phase_a(k + 2, xa, ea);
-        phase_b(k + 1, xb, eb);
-      }
-    }
-  }
-}
-
-// elements behind the last full 128-byte row (fewer than 128 / sizeof(A)); runs after scan_tb_kernel on the stream
-template <typename A>
-__global__ void scan_tb_tail_kernel(const A* in, A* out, size_t n_main, size_t n, int exclusive, const typename Desc<A>::word* total_slot) {
-  if(threadIdx.x != 0 || blockIdx.x != 0) return;
-  uint32_t st;
-  A run;
-  Desc<A>::load(total_slot, st, run);  // seed + sum of the first n_main elements (in and out may be the same buffer)
-  for(size_t i = n_main; i < n; ++i) {
-    const A x = in[i];
-    if(exclusive) out[i] = run;
-    run += x;
-    if(!exclusive) out[i] = run;
-  }
-}
-
 // co-resident CTAs per SM of a persistent kernel instantiation.  The shared-memory opt-in is a per-device
 // function attribute, so the query (and the opt-in) is made once per device, on the current device.
 constexpr int SB_MAX_DEVICES = 64;
@@ -1296,10 +604,12 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
     size_t g = (size_t)ctx->sm_count * ind_per_sm;
     if(g > tiles) g = tiles;
     // every CTA's producer draws tickets until one is past the last tile: tiles + grid tickets per launch
+    // (the host mirror of the ticket advances only once the launch is known to have been accepted)
     const unsigned long long tbase = ctx->scan_ticket_base;
-    ctx->scan_ticket_base += tiles + g;
     scan_independent_kernel<A, MODE, K, NW><<<(unsigned)g, (NW + 1) * 32, smem, ctx->stream>>>(in, out, n, exclusive, seg_len, seg_mask, flags,
         num_tiles, flags_in_ring, ctx->scan_ticket, tbase);
+    if(cudaError_t e = cudaGetLastError(); e != cudaSuccess) return (int)e;
+    ctx->scan_ticket_base += tiles + g;
     return SB_OK;
   }
   // Cooperative launch: the runtime guarantees that all CTAs of the grid are co-resident (or refuses the
@@ -1308,59 +618,6 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
       (void*)&desc, (void*)&epoch, (void*)&use_lookback, (void*)&num_tiles, (void*)&flags_in_ring};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_ws_kernel<A, MODE, K, NW>, dim3((unsigned)grid), dim3(WS_THREADS), args, smem, ctx->stream);
   if(e != cudaSuccess) return (int)e;
-  return SB_OK;
-}
-
-// ---- host side of kernel 4: tensor maps + cooperative launch ---------------------------------------------------
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn tensor_map_encoder() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-    (void)cudaGetLastError();
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-// [rows][128 bytes] view of a 16-byte aligned array, box = 256 rows, 128-byte swizzle
-bool make_row_map(CUtensorMap* tm, const void* base, unsigned long long rows) {
-  EncodeTiledFn enc = tensor_map_encoder();
-  if(!enc) return false;
-  const cuuint64_t dims[2] = {32, rows};          // 32 x u32 = 128 bytes per row
-  const cuuint64_t strides[1] = {128};            // bytes between rows
-  const cuuint32_t box[2] = {32, TB_BOX_ROWS};
-  const cuuint32_t estr[2] = {1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// returns SB_ERR_UNSUPPORTED when the tensor-map path is not available (caller falls back to scan_ws_kernel)
-template <typename A>
-int launch_tb(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, const A* seed, typename Desc<A>::word* desc, uint32_t epoch, size_t tiles) {
-  constexpr size_t E = 128 / sizeof(A);
-  const unsigned long long rows = n / E;
-  if(rows == 0 || rows >= 0xffffffffull) return SB_ERR_UNSUPPORTED;
-  alignas(64) CUtensorMap tm_in, tm_out;
-  if(!make_row_map(&tm_in, in, rows) || !make_row_map(&tm_out, out, rows)) return SB_ERR_UNSUPPORTED;
-  constexpr size_t smem = (size_t)(TB_STAGES + 1) * TB_STAGE_BYTES + 1024;  // ring + staging tile + alignment slack
-  static OccupancyCache cache;
-  const int per_sm = resident_ctas_per_sm(cache, ctx->device, scan_tb_kernel<A>, TB_THREADS, smem);
-  if(per_sm <= 0) return SB_ERR_UNSUPPORTED;
-  const long long num_tiles = (long long)((rows + TB_ROWS - 1) / TB_ROWS);
-  size_t grid = (size_t)ctx->sm_count;  // one CTA per SM (launch bounds)
-  if((long long)grid > num_tiles) grid = (size_t)num_tiles;
-  long long total_rows = (long long)rows;
-  typename Desc<A>::word* total_slot = desc + 2 * tiles + 32;  // scratch behind the tile and round descriptors
-  void* args[] = {(void*)&tm_in, (void*)&tm_out, (void*)&total_rows, (void*)&exclusive, (void*)&seed, (void*)&desc, (void*)&total_slot, (void*)&epoch, (void*)&num_tiles};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_tb_kernel<A>, dim3((unsigned)grid), dim3(TB_THREADS), args, smem, ctx->stream);
-  if(e != cudaSuccess) return (int)e;
-  const size_t n_main = (size_t)rows * E;
-  if(n_main < n) {
-    ctx->launches++;
-    scan_tb_tail_kernel<A><<<1, 32, 0, ctx->stream>>>(in, out, n_main, n, exclusive, total_slot);
-  }
   return SB_OK;
 }
 
@@ -1413,27 +670,13 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
     }
     epoch = ++ctx->scan_epoch;
     desc = reinterpret_cast<W*>(sizeof(A) == 4 ? ctx->desc64 : ctx->desc128);
-    if(!use_ws) {
-      tbase = ctx->scan_ticket_base;
-      ctx->scan_ticket_base += tiles;
-    }
+    if(!use_ws) tbase = ctx->scan_ticket_base;  // advanced after the launch succeeded
   }
   const A* ain = reinterpret_cast<const A*>(in);
   A* aout = reinterpret_cast<A*>(out);
   const A* aseed = reinterpret_cast<const A*>(seed);
   if(use_ws) {
     int rc;
-    // global scans: SB_SCAN_TB=1 selects the experimental thread-blocked kernel on swizzled TMA tensor tiles
-    // (parity-green, currently slower than the row-per-warp kernel: DESIGN.md section 4.4)
-    static const bool tb_enabled = getenv("SB_SCAN_TB") && getenv("SB_SCAN_TB")[0] == '1';
-    if(mode == MODE_PLAIN && use_lookback && tb_enabled) {
-      rc = launch_tb<A>(ctx, ain, aout, n, exclusive, aseed, desc, epoch, tiles);
-      if(rc == SB_OK) {
-        SB_CHECK_LAUNCH(ctx);
-        return SB_OK;
-      }
-      if(rc != SB_ERR_UNSUPPORTED) return rc;
-    }
     if(mode == MODE_PLAIN) rc = launch_ws<A, MODE_PLAIN, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && wide) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && narrow) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_NARROW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
@@ -1456,6 +699,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   }
 #undef SB_SCAN_LAUNCH
   SB_CHECK_LAUNCH(ctx);
+  if(use_lookback) ctx->scan_ticket_base += tiles;
   return SB_OK;
 }
 
@@ -1476,13 +720,7 @@ int segscan_impl(sb_ctx* ctx, const T* in, T* out, size_t n, size_t seg_len, con
 
 }  // namespace
 
-#ifdef SB_TB_TRACE
-extern "C" __attribute__((visibility("default"))) int sb_tb_trace_dump(unsigned long long* dst) {
-  return (int)cudaMemcpyFromSymbol(dst, tb_trace, sizeof(tb_trace));
-}
-#endif
-
-size_t sb_scan_tile_bytes() { return (size_t)WS_NW * WS_K * 512; }
+size_t sb_scan_min_tile_bytes() { return (size_t)(SCAN_NT / 32) * SCAN_K * 512; }  // the ticketed kernel's 16 KB tile
 
 extern "C" {
 int sb_scan_i32(sb_ctx* c, const int32_t* in, int32_t* out, size_t n, int ex, size_t g, const int32_t* seed) { return scan_impl<int32_t>(c, in, out, n, ex, g, seed); }

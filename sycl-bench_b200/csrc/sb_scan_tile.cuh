@@ -1,0 +1,418 @@
+// Device building blocks shared by the scan kernels (sb_scan.cu, sb_scan_cyclic.cu): tile geometry, tile
+// descriptors, mbarrier / TMA bulk-copy primitives and the per-warp row scans.  See sb_scan.cu for the design.
+#pragma once
+#include "sb_common.cuh"
+
+namespace sbscan {
+
+enum : uint32_t { ST_AGG = 1u, ST_INCL = 2u };
+enum { MODE_PLAIN = 0, MODE_IMPLICIT = 1, MODE_FLAGS = 2 };
+
+template <typename A, int NW_, int K> struct TileCfg {
+  static constexpr int VEC = 16 / sizeof(A);
+  static constexpr int NW = NW_;
+  static constexpr int ROW = 32 * VEC;      // elements one warp covers with one 128-bit access per lane
+  static constexpr int WCHUNK = K * ROW;    // consecutive elements owned by a warp
+  static constexpr int TILE = NW * WCHUNK;  // elements per tile
+  static constexpr int TILE_BYTES = NW * K * 512;
+};
+
+// ---- descriptors ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bits_of(uint32_t v) { return v; }
+__device__ __forceinline__ uint32_t bits_of(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ unsigned long long bits_of(unsigned long long v) { return v; }
+__device__ __forceinline__ unsigned long long bits_of(double v) { return (unsigned long long)__double_as_longlong(v); }
+template <typename A> __device__ __forceinline__ A from_bits32(uint32_t b);
+template <> __device__ __forceinline__ uint32_t from_bits32<uint32_t>(uint32_t b) { return b; }
+template <> __device__ __forceinline__ float from_bits32<float>(uint32_t b) { return __uint_as_float(b); }
+template <typename A> __device__ __forceinline__ A from_bits64(unsigned long long b);
+template <> __device__ __forceinline__ unsigned long long from_bits64<unsigned long long>(unsigned long long b) { return b; }
+template <> __device__ __forceinline__ double from_bits64<double>(unsigned long long b) { return __longlong_as_double((long long)b); }
+
+template <typename A, int BYTES = sizeof(A)> struct Desc;
+
+template <typename A> struct Desc<A, 4> {
+  using word = unsigned long long;
+  static __device__ __forceinline__ void store(word* d, uint32_t status, A v) {
+    const word w = ((word)bits_of(v) << 32) | status;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(d), "l"(w) : "memory");
+  }
+  static __device__ __forceinline__ void load(const word* d, uint32_t& status, A& v) {
+    word w;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(d) : "memory");
+    status = (uint32_t)w;
+    v = from_bits32<A>((uint32_t)(w >> 32));
+  }
+};
+
+struct alignas(16) desc128_t { unsigned long long status, value; };
+
+template <typename A> struct Desc<A, 8> {
+  using word = desc128_t;
+  static __device__ __forceinline__ void store(word* d, uint32_t status, A v) {
+    const unsigned long long s = status, b = bits_of(v);
+    asm volatile("{.reg .b128 t; mov.b128 t, {%1,%2}; st.relaxed.gpu.global.b128 [%0], t;}" ::"l"(d), "l"(s), "l"(b) : "memory");
+  }
+  static __device__ __forceinline__ void load(const word* d, uint32_t& status, A& v) {
+    unsigned long long s, b;
+    asm volatile("{.reg .b128 t; ld.relaxed.gpu.global.b128 t, [%2]; mov.b128 {%0,%1}, t;}" : "=l"(s), "=l"(b) : "l"(d) : "memory");
+    status = (s >> 32) ? 0u : (uint32_t)s;
+    v = from_bits64<A>(b);
+  }
+};
+
+// ---- mbarrier / TMA bulk-copy primitives ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while(!done) {
+    asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p;}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, unsigned long long policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+
+// ---- per-warp building blocks ---------------------------------------------------------------------------------
+// head flags of the K x VEC elements a thread owns (bit c of hf[j] = element c of row j is a head)
+template <typename A, int MODE, int K>
+__device__ __forceinline__ void tile_head_flags(unsigned (&hf)[K], size_t wbase, size_t n, size_t seg_len, size_t seg_mask,
+    const uint8_t* __restrict__ flags) {
+  constexpr int VEC = 16 / sizeof(A);
+  constexpr int ROW = 32 * VEC;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    const size_t idx = wbase + (size_t)j * ROW;
+    hf[j] = 0;
+    if(MODE == MODE_IMPLICIT) {
+      if(seg_mask != ~(size_t)0) {
+        if(seg_mask >= (size_t)(VEC - 1)) {
+          // power-of-two segment of at least one vector: only element 0 of an aligned vector can be a head
+          hf[j] = (idx & seg_mask) == 0 ? 1u : 0u;
+        } else {
+#pragma unroll
+          for(int c = 0; c < VEC; ++c) hf[j] |= (((idx + c) & seg_mask) == 0 ? 1u : 0u) << c;
+        }
+      } else {
+        size_t r = idx % seg_len;
+#pragma unroll
+        for(int c = 0; c < VEC; ++c) {
+          hf[j] |= (r == 0 ? 1u : 0u) << c;
+          r = (r + 1 == seg_len) ? 0 : r + 1;
+        }
+      }
+    } else if(MODE == MODE_FLAGS) {
+      if(idx + VEC <= n && (reinterpret_cast<uintptr_t>(flags + idx) & (VEC - 1)) == 0) {
+        uint32_t w;  // VEC flag bytes in one access
+        if(VEC == 4) w = __ldg(reinterpret_cast<const uint32_t*>(flags + idx));
+        else w = __ldg(reinterpret_cast<const uint16_t*>(flags + idx));
+#pragma unroll
+        for(int c = 0; c < VEC; ++c) hf[j] |= (((w >> (8 * c)) & 0xffu) ? 1u : 0u) << c;
+      } else {
+#pragma unroll
+        for(int c = 0; c < VEC; ++c) hf[j] |= ((idx + c < n && flags[idx + c]) ? 1u : 0u) << c;
+      }
+      if(idx == 0) hf[j] |= 1u;
+    }
+  }
+}
+
+// explicit head flags staged in the ring by the producer (one flag byte per element, warp chunk at `wflags`):
+// VEC bytes per lane and row, bank-conflict free
+template <typename A, int K>
+__device__ __forceinline__ void tile_head_flags_ring(unsigned (&hf)[K], const unsigned char* wflags, size_t wbase) {
+  constexpr int VEC = 16 / sizeof(A);
+  constexpr int ROW = 32 * VEC;
+  const unsigned char* fp = wflags + (threadIdx.x & 31) * VEC;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    uint32_t w;
+    if(VEC == 4) w = *reinterpret_cast<const uint32_t*>(fp + j * ROW);
+    else w = *reinterpret_cast<const uint16_t*>(fp + j * ROW);
+    hf[j] = 0;
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) hf[j] |= (((w >> (8 * c)) & 0xffu) ? 1u : 0u) << c;
+    if(wbase + (size_t)j * ROW == 0) hf[j] |= 1u;  // element 0 always starts a segment
+  }
+}
+
+// guarded global -> register load of a (possibly partial, possibly unaligned) tile
+template <typename A, bool ALIGNED, int K>
+__device__ __forceinline__ void tile_load_global(A (&v)[K][16 / sizeof(A)], const A* in, size_t wbase, bool full_tile, size_t n) {
+  constexpr int VEC = 16 / sizeof(A);
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    const size_t idx = wbase + (size_t)j * (32 * VEC);
+    if(ALIGNED && (full_tile || idx + VEC <= n)) {
+      sb::Vec<A> t = sb::ldg_stream<A>(in + idx);
+#pragma unroll
+      for(int c = 0; c < VEC; ++c) v[j][c] = t.v[c];
+    } else {
+#pragma unroll
+      for(int c = 0; c < VEC; ++c) v[j][c] = (idx + c < n) ? in[idx + c] : A(0);
+    }
+  }
+}
+
+// shared-memory ring -> registers (the lane-consecutive 16-byte layout is bank-conflict free)
+template <typename A, int K>
+__device__ __forceinline__ void tile_load_smem(A (&v)[K][16 / sizeof(A)], const unsigned char* warp_rows) {
+  constexpr int VEC = 16 / sizeof(A);
+  const unsigned char* sp = warp_rows + (threadIdx.x & 31) * 16;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    const sb::Vec<A> t = *reinterpret_cast<const sb::Vec<A>*>(sp + (size_t)j * 512);
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) v[j][c] = t.v[c];
+  }
+}
+
+// the warp's K rows reduced to (sum since the last head, contains a head)
+template <typename A, int MODE, int K>
+__device__ __forceinline__ void warp_reduce_rows(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A& agg, bool& has_head) {
+  constexpr int VEC = 16 / sizeof(A);
+  const int lane = threadIdx.x & 31;
+  if(MODE == MODE_PLAIN) {
+    A s = A(0);
+#pragma unroll
+    for(int j = 0; j < K; ++j) {
+      A r = v[j][0];
+#pragma unroll
+      for(int c = 1; c < VEC; ++c) r += v[j][c];
+      s += r;
+    }
+    agg = sb::warp_sum<A>(s);
+    has_head = false;
+    return;
+  }
+  {
+    unsigned any = 0;
+#pragma unroll
+    for(int j = 0; j < K; ++j) any |= hf[j];
+    if(!__any_sync(SB_FULL_MASK, any != 0u)) {  // no head in the warp chunk: one warp sum instead of K
+      warp_reduce_rows<A, MODE_PLAIN, K>(v, hf, agg, has_head);
+      return;
+    }
+  }
+  A run = A(0);
+  bool runf = false;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    A s = A(0);
+    bool f = false;
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) {
+      if((hf[j] >> c) & 1u) {
+        s = v[j][c];
+        f = true;
+      } else {
+        s += v[j][c];
+      }
+    }
+    const unsigned hm = __ballot_sync(SB_FULL_MASK, f);
+    if(hm) {
+      const int hl = 31 - __clz(hm);
+      run = sb::warp_sum<A>(lane >= hl ? s : A(0));
+      runf = true;
+    } else {
+      run += sb::warp_sum<A>(s);
+    }
+  }
+  agg = run;
+  has_head = runf;
+}
+
+// pass 1: thread partials -> per-row warp segmented scan.  The K row scans are independent shuffle
+// chains (the compiler interleaves them: ILP K); the carries between rows are added afterwards.
+// carry_in[j] = running sum entering the thread's part of row j, relative to the start of the warp
+// chunk (or the last head inside it); open[j] = no head between the start of the chunk and there.
+// Segmented variant of pass 1 with the row scans chained through the carry: fewer live registers
+// (no per-row totals / head masks), which matters more than ILP once head flags are in play.
+template <typename A, int MODE, int K>
+__device__ __forceinline__ void tile_pass1_chained(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A (&carry_in)[K],
+    bool (&open)[K], A& warp_agg, bool& warp_has_head) {
+  constexpr int VEC = 16 / sizeof(A);
+  const int lane = threadIdx.x & 31;
+  A row_carry = A(0);
+  bool warp_open = true;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    A s = A(0);
+    bool f = false;
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) {
+      if((hf[j] >> c) & 1u) {
+        s = v[j][c];
+        f = true;
+      } else {
+        s += v[j][c];
+      }
+    }
+    const unsigned hm = __ballot_sync(SB_FULL_MASK, f);
+    const unsigned m = hm & (0xffffffffu >> (31 - lane));
+    const int h = m ? 31 - __clz(m) : 0;
+    if(lane == 0 && !f) s += row_carry;
+    A inc = s;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1) {
+      const A t = sb::shfl_up(inc, d);
+      if(lane >= h + d) inc += t;
+    }
+    A ex = sb::shfl_up(inc, 1);
+    if(lane == 0) ex = row_carry;
+    carry_in[j] = ex;
+    open[j] = warp_open && (hm & ((1u << lane) - 1u)) == 0u;
+    row_carry = sb::shfl_idx(inc, 31);
+    if(hm) warp_open = false;
+  }
+  warp_agg = row_carry;
+  warp_has_head = !warp_open;
+}
+
+template <typename A, int MODE, int K>
+__device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A (&carry_in)[K], bool (&open)[K],
+    A& warp_agg, bool& warp_has_head) {
+  if(MODE != MODE_PLAIN) {
+    // a warp chunk without any head (the common case once segments are longer than K rows) is a plain scan:
+    // take the unchained path, whose K row scans are independent shuffle chains
+    unsigned any = 0;
+#pragma unroll
+    for(int j = 0; j < K; ++j) any |= hf[j];
+    if(!__any_sync(SB_FULL_MASK, any != 0u)) {
+      tile_pass1<A, MODE_PLAIN, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+      return;
+    }
+    tile_pass1_chained<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+    return;
+  }
+  constexpr int VEC = 16 / sizeof(A);
+  const int lane = threadIdx.x & 31;
+  A tot[K];          // row sum since the last head of the row (whole row if it has none)
+  unsigned hm[K];    // lanes of row j that contain a head
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    A s = A(0);
+    bool f = false;
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) {
+      if(MODE != MODE_PLAIN && ((hf[j] >> c) & 1u)) {
+        s = v[j][c];
+        f = true;
+      } else {
+        s += v[j][c];
+      }
+    }
+    hm[j] = 0;
+    int h = 0;
+    if(MODE != MODE_PLAIN) {
+      hm[j] = __ballot_sync(SB_FULL_MASK, f);
+      const unsigned m = hm[j] & (0xffffffffu >> (31 - lane));
+      h = m ? 31 - __clz(m) : 0;
+    }
+    A inc = s;
+    if(MODE == MODE_PLAIN) {
+      sb::warp_inclusive_scan<A>(inc);  // predicated shuffle-adds
+    } else {
+#pragma unroll
+      for(int d = 1; d < 32; d <<= 1) {
+        const A t = sb::shfl_up(inc, d);
+        if(lane >= h + d) inc += t;
+      }
+    }
+    const A ex = sb::shfl_up(inc, 1);
+    carry_in[j] = lane == 0 ? A(0) : ex;
+    tot[j] = sb::shfl_idx(inc, 31);
+  }
+  A off = A(0);
+  bool warp_open = true;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    const bool row_open = MODE == MODE_PLAIN || (hm[j] & ((1u << lane) - 1u)) == 0u;  // no head in front of me in this row
+    if(row_open) carry_in[j] += off;
+    open[j] = warp_open && row_open;
+    if(MODE != MODE_PLAIN && hm[j]) {
+      off = tot[j];
+      warp_open = false;
+    } else {
+      off += tot[j];
+    }
+  }
+  warp_agg = off;
+  warp_has_head = !warp_open;
+}
+
+// pass 2: rescan with the known carry, 128-bit coalesced stores from registers
+// (HINT: the 128-bit stores carry an L2 cache policy, see sb_scan_cyclic.cu)
+template <typename A, int MODE, bool ALIGNED, int K, bool HINT = false>
+__device__ __forceinline__ void tile_pass2_store(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], const A (&carry_in)[K],
+    const bool (&open)[K], A warp_prefix, size_t wbase, bool full_tile, size_t n, A* out, int exclusive, unsigned long long policy = 0) {
+  constexpr int VEC = 16 / sizeof(A);
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    const size_t idx = wbase + (size_t)j * (32 * VEC);
+    A r = carry_in[j] + (open[j] ? warp_prefix : A(0));
+    sb::Vec<A> o;
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) {
+      if(MODE != MODE_PLAIN && ((hf[j] >> c) & 1u)) r = A(0);
+      const A e = r;
+      r += v[j][c];
+      o.v[c] = exclusive ? e : r;
+    }
+    if(ALIGNED && (full_tile || idx + VEC <= n)) {
+      if(HINT) {
+        const uint4& w = *reinterpret_cast<const uint4*>(&o);
+        asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(out + idx), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w), "l"(policy) : "memory");
+      } else {
+        sb::stg_vec<A>(out + idx, o);
+      }
+    } else {
+#pragma unroll
+      for(int c = 0; c < VEC; ++c)
+        if(idx + c < n) out[idx + c] = o.v[c];
+    }
+  }
+}
+
+// prefix of the warps in front of `warp` inside a tile and the tile's own (aggregate, has-head)
+template <typename A, int MODE, int NW>
+__device__ __forceinline__ void combine_warps(const A* wagg, const int* wflag, int warp, A& my_prefix, bool& my_open, A& tile_agg,
+    bool& tile_has_head) {
+  A run = A(0);
+  bool run_open = true;
+  my_prefix = A(0);
+  my_open = true;
+#pragma unroll
+  for(int u = 0; u < NW; ++u) {
+    if(u == warp) {
+      my_prefix = run;
+      my_open = run_open;
+    }
+    if(MODE != MODE_PLAIN && wflag[u]) {
+      run = wagg[u];
+      run_open = false;
+    } else {
+      run += wagg[u];
+    }
+  }
+  tile_agg = run;
+  tile_has_head = !run_open;
+}
+
+}  // namespace sbscan

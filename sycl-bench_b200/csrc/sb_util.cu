@@ -12,20 +12,35 @@ constexpr int UT_NT = 256;
 
 template <typename A> __device__ __forceinline__ A cast_index(unsigned long long g) { return (A)g; }
 
+// Where local element i of a shard sits in the global array.  block == 0: contiguous shard starting at `offset`.
+// block > 0: block-cyclic layout of sb_scan_cyclic (include/sb_cuda.h): blocks of `block` elements, block k on rank
+// k % world, a rank stores its blocks back to back; every rank holds the same n elements, so the blocks of the last
+// round are all `last_len` = n % block long and follow each other in rank order.
+struct Layout {
+  unsigned long long offset, block, full, last_len;
+  unsigned world, rank;
+  __device__ __forceinline__ unsigned long long global(size_t i) const {
+    if(block == 0) return offset + i;
+    const unsigned long long b = i / block, j = i - b * block;
+    if(b < full) return (b * world + rank) * block + j;
+    return full * world * block + rank * last_len + j;
+  }
+};
+
 template <typename A>
-__global__ void __launch_bounds__(UT_NT) iota_kernel(A* __restrict__ out, size_t n, unsigned long long offset, int aligned) {
+__global__ void __launch_bounds__(UT_NT) iota_kernel(A* __restrict__ out, size_t n, Layout lay, int aligned) {
   constexpr int VEC = 16 / sizeof(A);
   const size_t stride = (size_t)gridDim.x * UT_NT * VEC;
   for(size_t i = ((size_t)blockIdx.x * UT_NT + threadIdx.x) * VEC; i < n; i += stride) {
     if(aligned && i + VEC <= n) {
       sb::Vec<A> v;
 #pragma unroll
-      for(int c = 0; c < VEC; ++c) v.v[c] = cast_index<A>(offset + i + c);
+      for(int c = 0; c < VEC; ++c) v.v[c] = cast_index<A>(lay.global(i + c));
       sb::stg_vec<A>(out + i, v);
     } else {
 #pragma unroll
       for(int c = 0; c < VEC; ++c)
-        if(i + c < n) out[i + c] = cast_index<A>(offset + i + c);
+        if(i + c < n) out[i + c] = cast_index<A>(lay.global(i + c));
     }
   }
 }
@@ -108,23 +123,53 @@ __device__ __forceinline__ unsigned long long tri(unsigned long long g) {
   return (g & 1ull) ? g * ((g + 1ull) >> 1) : (g >> 1) * (g + 1ull);
 }
 
+// closed forms of SURVEY.md A.4 as exact integers mod 2^64 ...
+__device__ __forceinline__ unsigned long long expect_int(unsigned long long g, int kind, unsigned long long seg_len) {
+  if(seg_len == 0) return (kind == 0) ? tri(g) : (g == 0 ? 0ull : tri(g - 1ull));
+  const unsigned long long q = g / seg_len, j = g - q * seg_len;
+  if(kind == 0) return q * seg_len * (j + 1ull) + tri(j);
+  if(kind == 1) return q * seg_len * j + (j == 0 ? 0ull : tri(j - 1ull));
+  return (j == 0) ? q * seg_len * seg_len + tri(seg_len - 1ull) : g;
+}
+// ... and in double precision (the values exceed 2^64 for g > 2^32; relative error of the evaluation ~1e-16)
+__device__ __forceinline__ double trid(unsigned long long g) { return 0.5 * (double)g * ((double)g + 1.0); }
+__device__ __forceinline__ double expect_fp(unsigned long long g, int kind, unsigned long long seg_len, bool& exact) {
+  exact = false;
+  if(seg_len == 0) return (kind == 0) ? trid(g) : (g == 0 ? 0.0 : trid(g - 1ull));
+  const unsigned long long q = g / seg_len, j = g - q * seg_len;
+  const double base = (double)q * (double)seg_len;
+  if(kind == 0) return base * ((double)j + 1.0) + trid(j);
+  if(kind == 1) return base * (double)j + (j == 0 ? 0.0 : trid(j - 1ull));
+  if(j == 0) return base * (double)seg_len + trid(seg_len - 1ull);
+  exact = true;  // segmented-reduction layout: everything but the head is the untouched input
+  return (double)g;
+}
+
+template <typename A> struct is_fp { static constexpr bool value = false; };
+template <> struct is_fp<float> { static constexpr bool value = true; };
+template <> struct is_fp<double> { static constexpr bool value = true; };
+
+// Integer types: bit-exact (mod 2^w).  Floating point: |data - closed form| <= rel_tol * max(|closed form|, 1); the
+// untouched elements of the segmented-reduction layout must equal the input (T)g exactly.
 template <typename A>
-__global__ void __launch_bounds__(UT_NT) check_iota_kernel(const A* __restrict__ data, size_t n, unsigned long long offset, int kind,
-    unsigned long long seg_len, unsigned long long* __restrict__ mismatches) {
+__global__ void __launch_bounds__(UT_NT) check_iota_kernel(const A* __restrict__ data, size_t n, Layout lay, int kind,
+    unsigned long long seg_len, double rel_tol, unsigned long long* __restrict__ mismatches) {
   unsigned int bad = 0;
   const size_t stride = (size_t)gridDim.x * UT_NT;
   for(size_t i = (size_t)blockIdx.x * UT_NT + threadIdx.x; i < n; i += stride) {
-    const unsigned long long g = offset + i;
-    unsigned long long expect;
-    if(seg_len == 0) {
-      expect = (kind == 0) ? tri(g) : (g == 0 ? 0ull : tri(g - 1ull));
+    const unsigned long long g = lay.global(i);
+    if(is_fp<A>::value) {
+      bool exact;
+      const double want = expect_fp(g, kind, seg_len, exact);
+      const double got = (double)data[i];
+      if(exact) {
+        if(data[i] != cast_index<A>(g)) ++bad;
+      } else if(!(fabs(got - want) <= rel_tol * fmax(fabs(want), 1.0))) {  // the negation also catches NaN
+        ++bad;
+      }
     } else {
-      const unsigned long long q = g / seg_len, j = g - q * seg_len;
-      if(kind == 0) expect = q * seg_len * (j + 1ull) + tri(j);
-      else if(kind == 1) expect = q * seg_len * j + (j == 0 ? 0ull : tri(j - 1ull));
-      else expect = (j == 0) ? q * seg_len * seg_len + tri(seg_len - 1ull) : g;
+      if(data[i] != (A)expect_int(g, kind, seg_len)) ++bad;
     }
-    if(data[i] != (A)expect) ++bad;
   }
   bad = __reduce_add_sync(SB_FULL_MASK, bad);
   if((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, (unsigned long long)bad);
@@ -142,7 +187,7 @@ size_t grid_for(sb_ctx* ctx, size_t work_items, size_t per_block) {
 }
 
 template <typename T>
-int iota_impl(sb_ctx* ctx, T* out, size_t n, uint64_t offset) {
+int iota_impl(sb_ctx* ctx, T* out, size_t n, Layout lay) {
   using A = typename sb_arith<T>::type;
   if(!ctx || (n && !out)) return SB_ERR_BAD_ARG;
   if(!sb::aligned_to(out, sizeof(T))) return SB_ERR_MISALIGNED;
@@ -150,7 +195,7 @@ int iota_impl(sb_ctx* ctx, T* out, size_t n, uint64_t offset) {
   sb_device_guard guard(ctx->device);
   constexpr int VEC = 16 / sizeof(T);
   const size_t blocks = grid_for(ctx, n, (size_t)UT_NT * VEC);
-  iota_kernel<A><<<(unsigned)blocks, UT_NT, 0, ctx->stream>>>(reinterpret_cast<A*>(out), n, offset, sb::aligned_to(out, 16) ? 1 : 0);
+  iota_kernel<A><<<(unsigned)blocks, UT_NT, 0, ctx->stream>>>(reinterpret_cast<A*>(out), n, lay, sb::aligned_to(out, 16) ? 1 : 0);
   SB_CHECK_LAUNCH(ctx);
   return SB_OK;
 }
@@ -195,34 +240,51 @@ int exclusive_carry_impl(sb_ctx* ctx, const T* totals, int rank, T* carry_out) {
 }
 
 template <typename T>
-int check_impl(sb_ctx* ctx, const T* data, size_t n, uint64_t offset, int kind, size_t seg_len, uint64_t* mismatches) {
+int check_impl(sb_ctx* ctx, const T* data, size_t n, Layout lay, int kind, size_t seg_len, double rel_tol, uint64_t* mismatches) {
   using A = typename sb_arith<T>::type;
-  if(!ctx || !mismatches || (n && !data) || kind < 0 || kind > 2) return SB_ERR_BAD_ARG;
+  if(!ctx || !mismatches || (n && !data) || kind < 0 || kind > 2 || !(rel_tol >= 0.0)) return SB_ERR_BAD_ARG;
   if(kind == 2 && (seg_len == 0 || !sb::is_pow2(seg_len))) return SB_ERR_SEG_LEN;
   sb_device_guard guard(ctx->device);
   SB_CUDA_TRY(cudaMemsetAsync(mismatches, 0, sizeof(uint64_t), ctx->stream));
   if(n == 0) return SB_OK;
   const size_t blocks = grid_for(ctx, n, (size_t)UT_NT * 8);
   check_iota_kernel<A><<<(unsigned)blocks, UT_NT, 0, ctx->stream>>>(
-      reinterpret_cast<const A*>(data), n, offset, kind, seg_len, reinterpret_cast<unsigned long long*>(mismatches));
+      reinterpret_cast<const A*>(data), n, lay, kind, seg_len, rel_tol, reinterpret_cast<unsigned long long*>(mismatches));
   SB_CHECK_LAUNCH(ctx);
   return SB_OK;
+}
+
+inline Layout contiguous(uint64_t offset) { return Layout{offset, 0ull, 0ull, 0ull, 1u, 0u}; }
+inline bool cyclic_ok(size_t block, int world, int rank) { return block > 0 && world >= 1 && rank >= 0 && rank < world; }
+inline Layout cyclic(size_t n, size_t block, int world, int rank) {
+  return Layout{0ull, (unsigned long long)block, (unsigned long long)(n / block), (unsigned long long)(n % block), (unsigned)world, (unsigned)rank};
 }
 
 }  // namespace
 
 extern "C" {
-int sb_iota_i16(sb_ctx* c, int16_t* o, size_t n, uint64_t off) { return iota_impl<int16_t>(c, o, n, off); }
-int sb_iota_i32(sb_ctx* c, int32_t* o, size_t n, uint64_t off) { return iota_impl<int32_t>(c, o, n, off); }
-int sb_iota_i64(sb_ctx* c, int64_t* o, size_t n, uint64_t off) { return iota_impl<int64_t>(c, o, n, off); }
-int sb_iota_f32(sb_ctx* c, float* o, size_t n, uint64_t off) { return iota_impl<float>(c, o, n, off); }
-int sb_iota_f64(sb_ctx* c, double* o, size_t n, uint64_t off) { return iota_impl<double>(c, o, n, off); }
+int sb_iota_i16(sb_ctx* c, int16_t* o, size_t n, uint64_t off) { return iota_impl<int16_t>(c, o, n, contiguous(off)); }
+int sb_iota_i32(sb_ctx* c, int32_t* o, size_t n, uint64_t off) { return iota_impl<int32_t>(c, o, n, contiguous(off)); }
+int sb_iota_i64(sb_ctx* c, int64_t* o, size_t n, uint64_t off) { return iota_impl<int64_t>(c, o, n, contiguous(off)); }
+int sb_iota_f32(sb_ctx* c, float* o, size_t n, uint64_t off) { return iota_impl<float>(c, o, n, contiguous(off)); }
+int sb_iota_f64(sb_ctx* c, double* o, size_t n, uint64_t off) { return iota_impl<double>(c, o, n, contiguous(off)); }
+#define SB_IOTA_CYCLIC(sfx, T)                                                                              \
+  int sb_iota_cyclic_##sfx(sb_ctx* c, T* o, size_t n, size_t block, int world, int rank) {                  \
+    if(!cyclic_ok(block, world, rank)) return SB_ERR_BAD_ARG;                                               \
+    return iota_impl<T>(c, o, n, cyclic(n, block, world, rank));                                               \
+  }
+SB_IOTA_CYCLIC(i32, int32_t)
+SB_IOTA_CYCLIC(i64, int64_t)
+SB_IOTA_CYCLIC(f32, float)
+SB_IOTA_CYCLIC(f64, double)
+#undef SB_IOTA_CYCLIC
 int sb_copy(sb_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if(!ctx || (bytes && (!dst || !src))) return SB_ERR_BAD_ARG;
   if(bytes == 0 || dst == src) return SB_OK;
   sb_device_guard guard(ctx->device);
   const unsigned char* s = static_cast<const unsigned char*>(src);
   unsigned char* d = static_cast<unsigned char*>(dst);
+  if(d < s + bytes && s < d + bytes) return SB_ERR_BAD_ARG;  // partially overlapping ranges (the kernel reads through the read-only path)
   const uintptr_t sa = reinterpret_cast<uintptr_t>(s) & 15, da = reinterpret_cast<uintptr_t>(d) & 15;
   if(sa != da) {  // no common 16-byte phase: byte copy
     copy_bytes_kernel<<<(unsigned)grid_for(ctx, bytes, UT_NT), UT_NT, 0, ctx->stream>>>(s, d, bytes);
@@ -264,6 +326,18 @@ int sb_exclusive_carry_i64(sb_ctx* c, const int64_t* t, int r, int64_t* o) { ret
 int sb_exclusive_carry_f32(sb_ctx* c, const float* t, int r, float* o) { return exclusive_carry_impl<float>(c, t, r, o); }
 int sb_exclusive_carry_f64(sb_ctx* c, const double* t, int r, double* o) { return exclusive_carry_impl<double>(c, t, r, o); }
 
-int sb_check_iota_i32(sb_ctx* c, const int32_t* d, size_t n, uint64_t off, int kind, size_t L, uint64_t* m) { return check_impl<int32_t>(c, d, n, off, kind, L, m); }
-int sb_check_iota_i64(sb_ctx* c, const int64_t* d, size_t n, uint64_t off, int kind, size_t L, uint64_t* m) { return check_impl<int64_t>(c, d, n, off, kind, L, m); }
+int sb_check_iota_i32(sb_ctx* c, const int32_t* d, size_t n, uint64_t off, int kind, size_t L, uint64_t* m) { return check_impl<int32_t>(c, d, n, contiguous(off), kind, L, 0.0, m); }
+int sb_check_iota_i64(sb_ctx* c, const int64_t* d, size_t n, uint64_t off, int kind, size_t L, uint64_t* m) { return check_impl<int64_t>(c, d, n, contiguous(off), kind, L, 0.0, m); }
+int sb_check_iota_f32(sb_ctx* c, const float* d, size_t n, uint64_t off, int kind, size_t L, double tol, uint64_t* m) { return check_impl<float>(c, d, n, contiguous(off), kind, L, tol, m); }
+int sb_check_iota_f64(sb_ctx* c, const double* d, size_t n, uint64_t off, int kind, size_t L, double tol, uint64_t* m) { return check_impl<double>(c, d, n, contiguous(off), kind, L, tol, m); }
+#define SB_CHECK_CYCLIC(sfx, T)                                                                                                        \
+  int sb_check_iota_cyclic_##sfx(sb_ctx* c, const T* d, size_t n, size_t block, int world, int rank, int kind, double tol, uint64_t* m) { \
+    if(!cyclic_ok(block, world, rank) || kind > 1) return SB_ERR_BAD_ARG;                                                              \
+    return check_impl<T>(c, d, n, cyclic(n, block, world, rank), kind, 0, tol, m);                                                        \
+  }
+SB_CHECK_CYCLIC(i32, int32_t)
+SB_CHECK_CYCLIC(i64, int64_t)
+SB_CHECK_CYCLIC(f32, float)
+SB_CHECK_CYCLIC(f64, double)
+#undef SB_CHECK_CYCLIC
 }

@@ -28,9 +28,33 @@ template <class T> struct Ops;
   static int iota(sb_ctx* c, T* out, size_t n, uint64_t off) { return sb_iota_##SUF(c, p(out), n, off); }               \
   static int segreduce(sb_ctx* c, T* buf, size_t n, size_t L) { return sb_segreduce_##SUF(c, p(buf), n, L); }
 
+// sb_check_iota_<T>: the integer entry points take no tolerance
+template <class ABI> struct CheckCall;
+template <> struct CheckCall<int32_t> {
+  static int call(sb_ctx* c, const int32_t* d, size_t n, uint64_t off, int kind, size_t L, double, uint64_t* bad) { return sb_check_iota_i32(c, d, n, off, kind, L, bad); }
+};
+template <> struct CheckCall<int64_t> {
+  static int call(sb_ctx* c, const int64_t* d, size_t n, uint64_t off, int kind, size_t L, double, uint64_t* bad) { return sb_check_iota_i64(c, d, n, off, kind, L, bad); }
+};
+template <> struct CheckCall<float> {
+  static int call(sb_ctx* c, const float* d, size_t n, uint64_t off, int kind, size_t L, double tol, uint64_t* bad) { return sb_check_iota_f32(c, d, n, off, kind, L, tol, bad); }
+};
+template <> struct CheckCall<double> {
+  static int call(sb_ctx* c, const double* d, size_t n, uint64_t off, int kind, size_t L, double tol, uint64_t* bad) { return sb_check_iota_f64(c, d, n, off, kind, L, tol, bad); }
+};
+
 #define SB_PATTERN_OPS_FULL(T, ABI, SUF)                                                                                \
   template <> struct Ops<T> {                                                                                           \
     SB_PATTERN_OPS_COMMON(T, ABI, SUF)                                                                                  \
+    static int check(sb_ctx* c, const T* d, size_t n, uint64_t off, int kind, size_t L, double tol, uint64_t* bad) {    \
+      return CheckCall<ABI>::call(c, p(d), n, off, kind, L, tol, bad);                                                  \
+    }                                                                                                                   \
+    static int iota_cyclic(sb_ctx* c, T* out, size_t n, size_t block, int world, int rank) {                            \
+      return sb_iota_cyclic_##SUF(c, p(out), n, block, world, rank);                                                    \
+    }                                                                                                                   \
+    static int check_cyclic(sb_ctx* c, const T* d, size_t n, size_t block, int world, int rank, int kind, double tol, uint64_t* bad) { \
+      return sb_check_iota_cyclic_##SUF(c, p(d), n, block, world, rank, kind, tol, bad);                                \
+    }                                                                                                                   \
     static int reduce(sb_ctx* c, const T* in, size_t n, T* out) { return sb_reduce_##SUF(c, p(in), n, p(out)); }        \
     static int scan(sb_ctx* c, const T* in, T* out, size_t n, int excl, size_t group) {                                 \
       return sb_scan_##SUF(c, p(in), p(out), n, excl, group, nullptr);                                                  \
@@ -85,37 +109,31 @@ inline bool value_matches(T got, uint64_t exact_mod64, long double exact_real, s
 }
 
 // ---- scan-family verification -------------------------------------------------------------------------------
-// integers: every element on the device against the closed form (sb_check_iota); floating point: the
-// first and last 2^16 elements plus 2^16 strided samples against the closed form within the tolerance.
-// `out` holds elements [offset, offset + n) of a scan over `total` elements (offset = 0, total = n unless sharded).
+// EVERY element on the device against the closed form (sb_check_iota_<T>): integers bit-exact, floating point
+// within the north-star tolerance.  `out` holds elements [offset, offset + n) of a scan over `total` elements
+// (offset = 0, total = n unless sharded).  kind: 0 inclusive scan, 1 exclusive scan, 2 segmented-reduction layout.
 template <class T>
-bool verify_scan(sb_ctx* ctx, const PrefetchedBuffer<T>& out, size_t n, bool exclusive, size_t L, size_t offset = 0, size_t total = 0) {
+bool verify_closed_form(sb_ctx* ctx, const T* data, size_t n, int kind, size_t L, size_t offset = 0, size_t total = 0) {
   if(n == 0) return true;
   if(total == 0) total = n;
-  if constexpr(std::is_same_v<T, int> || std::is_same_v<T, long long>) {
-    PrefetchedBuffer<unsigned long long> bad;
-    bad.initialize(ctx, 1);
-    int rc;
-    if constexpr(std::is_same_v<T, int>) rc = sb_check_iota_i32(ctx, reinterpret_cast<const int32_t*>(out.get()), n, offset, exclusive ? 1 : 0, L, reinterpret_cast<uint64_t*>(bad.get()));
-    else rc = sb_check_iota_i64(ctx, reinterpret_cast<const int64_t*>(out.get()), n, offset, exclusive ? 1 : 0, L, reinterpret_cast<uint64_t*>(bad.get()));
-    sb::check(rc, "sb_check_iota");
-    return bad.get_host_access()[0] == 0;
-  } else {
-    const size_t win = std::min<size_t>(n, size_t(1) << 16);
-    auto check_window = [&](size_t begin, size_t count) {
-      const auto h = out.get_host_access(begin, count);
-      for(size_t i = 0; i < count; ++i)
-        if(!value_matches<T>(h[i], 0, scan_value_ld(offset + begin + i, exclusive, L), total)) return false;
-      return true;
-    };
-    if(!check_window(0, win) || !check_window(n - win, win)) return false;
-    const size_t stride = std::max<size_t>(1, n / win);
-    for(size_t g = stride / 2; g < n; g += stride * 64) {
-      const size_t count = std::min<size_t>(64, n - g);
-      if(!check_window(g, count)) return false;
-    }
-    return true;
-  }
+  PrefetchedBuffer<unsigned long long> bad;
+  bad.initialize(ctx, 1);
+  sb::check(Ops<T>::check(ctx, data, n, offset, kind, L, (double)tolerance<T>(total), reinterpret_cast<uint64_t*>(bad.get())), "sb_check_iota");
+  return bad.get_host_access()[0] == 0;
+}
+template <class T>
+bool verify_scan(sb_ctx* ctx, const PrefetchedBuffer<T>& out, size_t n, bool exclusive, size_t L, size_t offset = 0, size_t total = 0) {
+  return verify_closed_form<T>(ctx, out.get(), n, exclusive ? 1 : 0, L, offset, total);
+}
+// the same for a shard of the block-cyclic layout of sb_scan_cyclic (global scans only)
+template <class T>
+bool verify_scan_cyclic(sb_ctx* ctx, const PrefetchedBuffer<T>& out, size_t n, bool exclusive, size_t block, int world, int rank) {
+  if(n == 0) return true;
+  PrefetchedBuffer<unsigned long long> bad;
+  bad.initialize(ctx, 1);
+  sb::check(Ops<T>::check_cyclic(ctx, out.get(), n, block, world, rank, exclusive ? 1 : 0, (double)tolerance<T>(n * (size_t)world), reinterpret_cast<uint64_t*>(bad.get())),
+            "sb_check_iota_cyclic");
+  return bad.get_host_access()[0] == 0;
 }
 
 } // namespace pattern

@@ -32,5 +32,6 @@ int main(int argc, char** argv) {
     app.run<ScanGroupNDRange<float>>();
     app.run<ScanGroupNDRange<double>>();
   }
+  pattern::release_comms();
   return app.exitCode();
 }

@@ -5,13 +5,17 @@
 // verify(): heads against the closed form g*L^2 + L(L-1)/2 (integers and fp64 exact — all partial
 // sums are integers below 2^53 — fp32 within 1e-5*log2 N), non-heads bit-identical to the input,
 // like upstream :107-119 but with a tolerance where upstream's exact `!=` cannot hold.
-#include "pattern_common.h"
+#include "sharded.h"
 
 template <typename T>
 class SegmentedReduction {
 protected:
   BenchmarkArgs _args;
   PrefetchedBuffer<T> _buff;
+  // --num-gpus=N: shards cut on segment boundaries, independent replicas (sb_comm_foreach); not for int16
+  int _gpus = 1;
+  sb_comm* _comm = nullptr;
+  pattern::ShardedArray<T> _shards;
 
 public:
   SegmentedReduction(const BenchmarkArgs& args) : _args{args} {}
@@ -19,29 +23,44 @@ public:
   void setup() {
     if(_args.local_size == 0 || _args.problem_size % _args.local_size != 0)
       throw std::invalid_argument("segmentedreduction: --size must be a multiple of --local (asserted upstream, segmentedreduction.cpp:23)");
+    _gpus = pattern::requested_gpus(_args);
+    if(_gpus > 1 && (std::is_same_v<T, short> || (_args.local_size & (_args.local_size - 1)) != 0)) {
+      // the int16 row and non-power-of-two --local (reference-tree subset, host-side check) stay on one GPU
+      _gpus = 1;
+    }
+    if(_gpus > 1) {
+      _comm = pattern::comm_for(_args, _gpus);
+      _shards.initialize(_comm, _args.problem_size, pattern::lcm16(_args.local_size));
+      _shards.fill_iota();
+      return;
+    }
     _buff.initialize(_args.ctx(), _args.problem_size);
     sb::check(pattern::Ops<T>::iota(_args.ctx(), _buff.get(), _args.problem_size, 0), "sb_iota");
   }
 
   void run(std::vector<sb::event>& events) {
+    if(_gpus > 1) {
+      sb::check(sb_comm_foreach(_comm, SB_OP_SEGREDUCE, dtype(), nullptr, _shards.out_ptrs(), _shards.counts(), _args.local_size, 0), "sb_comm_foreach");
+      events.push_back({"sb_comm_foreach"});
+      return;
+    }
     sb::check(pattern::Ops<T>::segreduce(_args.ctx(), _buff.get(), _args.problem_size, _args.local_size), "sb_segreduce");
     events.push_back({"sb_segreduce"});
   }
 
   bool verify(VerificationSetting&) {
     const std::size_t n = _args.problem_size, L = _args.local_size;
-    if((L & (L - 1)) != 0) return verify_on_host(true);  // the reference tree skips elements for such L
-    if constexpr(std::is_same_v<T, int> || std::is_same_v<T, long long>) {
-      PrefetchedBuffer<unsigned long long> bad;
-      bad.initialize(_args.ctx(), 1);
-      int rc;
-      if constexpr(std::is_same_v<T, int>) rc = sb_check_iota_i32(_args.ctx(), reinterpret_cast<const int32_t*>(_buff.get()), n, 0, 2, L, reinterpret_cast<uint64_t*>(bad.get()));
-      else rc = sb_check_iota_i64(_args.ctx(), reinterpret_cast<const int64_t*>(_buff.get()), n, 0, 2, L, reinterpret_cast<uint64_t*>(bad.get()));
-      sb::check(rc, "sb_check_iota");
-      return bad.get_host_access()[0] == 0;
-    } else {
-      return verify_on_host(false);
+    if constexpr(!std::is_same_v<T, short>) {
+      if(_gpus > 1) {  // every shard, every element, on its own device (power-of-two --local only, see setup())
+        for(int r = 0; r < _gpus; ++r)
+          if(!pattern::verify_closed_form<T>(sb_comm_ctx(_comm, r), _shards.shard(r).get(), _shards.count(r), 2, L, _shards.begin(r), n)) return false;
+        return true;
+      }
+      // every element on the device: heads against the closed form (integers exact, floating point within the
+      // tolerance), the rest bit-identical to the input
+      if((L & (L - 1)) == 0) return pattern::verify_closed_form<T>(_args.ctx(), _buff.get(), n, 2, L);
     }
+    return verify_on_host((L & (L - 1)) != 0);  // int16, and --local values for which the reference tree skips elements
   }
 
   static ThroughputMetric getThroughputMetric(const BenchmarkArgs& args) {
@@ -50,6 +69,10 @@ public:
   }
 
 private:
+  static constexpr int dtype() {
+    if constexpr(std::is_same_v<T, short>) return SB_I16;
+    else return pattern::DtypeOf<T>::value;
+  }
   static bool tree_member(std::size_t j, std::size_t L) {
     for(std::size_t i = L / 2; i > 0; i /= 2)
       if(j >= i) j -= i;
@@ -97,5 +120,6 @@ int main(int argc, char** argv) {
   } else {
     std::cerr << "segmentedreduction: --no-ndrange-kernels leaves nothing to run (see DESIGN.md)\n";
   }
+  pattern::release_comms();
   return app.exitCode();
 }

@@ -25,5 +25,6 @@ int main(int argc, char** argv) {
     app.run<SegmentedScanFlagsNDRange<float>>();
     app.run<SegmentedScanFlagsNDRange<double>>();
   }
+  pattern::release_comms();
   return app.exitCode();
 }

@@ -1,6 +1,10 @@
-// --num-gpus=N for pattern/reduction and pattern/prefixsum: the problem is cut into N contiguous shards,
-// shard r lives on device (--device-index + r), and sb_comm_reduce / sb_comm_scan (include/sb_cuda.h)
-// run the per-shard kernels plus ONE NCCL collective of one element per rank (BASELINE.json north_star).
+// --num-gpus=N: the problem is sharded over N devices, shard r lives on device (--device-index + r).
+//   reduction, prefixsum, scan --scan-scope=global : sb_comm_reduce / sb_comm_scan (include/sb_cuda.h).
+//       --scan-strategy=cyclic (default): block-cyclic shards, one pass over the input, the round totals cross NVLink
+//       inside the kernel; reduce_then_scan / scan_then_carry: contiguous shards + ONE NCCL collective of one element
+//       per rank (BASELINE.json north_star).
+//   segmentedreduction, segmentedscan, scan --scan-scope=group : shards cut on segment boundaries, independent
+//       replicas of the 1-GPU kernel (sb_comm_foreach), nothing is exchanged.
 // The reference has no multi-device mode; with --num-gpus=1 (the default) nothing here is used.
 #pragma once
 
@@ -42,19 +46,28 @@ inline void release_comms() {
   comm_table().clear();
 }
 
-// contiguous shard [begin, end) of `rank`; every shard but the last is a multiple of 16 elements, so each
-// shard base keeps the 16-byte alignment the vector paths of sb_reduce / sb_scan want
-inline std::pair<std::size_t, std::size_t> shard_bounds(std::size_t n, int world, int rank) {
+// contiguous shard [begin, end) of `rank`; every shard but the last is a multiple of `align` elements: 16 keeps the
+// 16-byte alignment the vector paths of sb_reduce / sb_scan want, the segment length cuts on segment boundaries
+inline std::pair<std::size_t, std::size_t> shard_bounds(std::size_t n, int world, int rank, std::size_t align = 16) {
   std::size_t per = (n + world - 1) / world;
-  per = (per + 15) / 16 * 16;
+  per = (per + align - 1) / align * align;
   const std::size_t begin = std::min(n, per * static_cast<std::size_t>(rank));
   return {begin, std::min(n, begin + per)};
+}
+inline std::size_t lcm16(std::size_t L) {
+  std::size_t a = L, b = 16;
+  while(b) {
+    const std::size_t t = a % b;
+    a = b;
+    b = t;
+  }
+  return L / a * 16;
 }
 
 template <class T>
 class ShardedArray {
 public:
-  void initialize(sb_comm* comm, std::size_t n) {
+  void initialize(sb_comm* comm, std::size_t n, std::size_t align = 16) {
     comm_ = comm;
     const int world = sb_comm_size(comm);
     shards_.clear();
@@ -62,7 +75,7 @@ public:
     count_.assign(world, 0);
     ptrs_.assign(world, nullptr);
     for(int r = 0; r < world; ++r) {
-      const auto [b, e] = shard_bounds(n, world, r);
+      const auto [b, e] = shard_bounds(n, world, r, align);
       begin_[r] = b;
       count_[r] = e - b;
       shards_.push_back(std::make_unique<PrefetchedBuffer<T>>());
@@ -82,6 +95,27 @@ public:
       shards_.push_back(std::make_unique<PrefetchedBuffer<T>>());
       shards_.back()->initialize(sb_comm_ctx(comm, r), 1);
       ptrs_[r] = shards_.back()->get();
+    }
+  }
+  // block-cyclic layout of sb_scan_cyclic: every rank holds n / world elements (n must be a multiple of world)
+  void initialize_cyclic(sb_comm* comm, std::size_t n) {
+    comm_ = comm;
+    const int world = sb_comm_size(comm);
+    if(n % world != 0) throw std::invalid_argument("--scan-strategy=cyclic needs --size to be a multiple of --num-gpus");
+    shards_.clear();
+    begin_.assign(world, 0);
+    count_.assign(world, n / world);
+    ptrs_.assign(world, nullptr);
+    for(int r = 0; r < world; ++r) {
+      shards_.push_back(std::make_unique<PrefetchedBuffer<T>>());
+      shards_.back()->initialize(sb_comm_ctx(comm, r), std::max<std::size_t>(count_[r], 1));
+      ptrs_[r] = shards_.back()->get();
+    }
+  }
+  void fill_iota_cyclic(std::size_t block) {
+    for(int r = 0; r < world(); ++r) {
+      sb::check(Ops<T>::iota_cyclic(sb_comm_ctx(comm_, r), shards_[r]->get(), count_[r], block, world(), r), "sb_iota_cyclic");
+      sb::check(sb_ctx_sync(sb_comm_ctx(comm_, r)), "sb_ctx_sync");
     }
   }
   void fill_iota() {

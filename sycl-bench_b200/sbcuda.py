@@ -93,6 +93,24 @@ def lib() -> C.CDLL:
         getattr(L, f"sb_exclusive_carry_{t}").argtypes = [vp, vp, i, vp]
     for t in ("i32", "i64"):
         getattr(L, f"sb_check_iota_{t}").argtypes = [vp, vp, sz, u64, i, sz, vp]
+    for t in ("f32", "f64"):
+        getattr(L, f"sb_check_iota_{t}").argtypes = [vp, vp, sz, u64, i, sz, C.c_double, vp]
+    for t in DTYPES[1:]:
+        getattr(L, f"sb_iota_cyclic_{t}").argtypes = [vp, vp, sz, sz, i, i]
+        getattr(L, f"sb_check_iota_cyclic_{t}").argtypes = [vp, vp, sz, sz, i, i, i, C.c_double, vp]
+        getattr(L, f"sb_scan_cyclic_{t}").argtypes = [vp, vp, vp, vp, sz, i, vp]
+    L.sb_scan_cyclic.argtypes = [vp, vp, i, vp, vp, sz, i]
+    L.sb_cyclic_block_elems.argtypes = [vp, i]
+    L.sb_cyclic_block_elems.restype = sz
+    L.sb_peer_create.argtypes = [vp, i, i, C.POINTER(vp)]
+    L.sb_peer_destroy.argtypes = [vp]
+    L.sb_peer_handle.argtypes = [vp, vp, sz]
+    L.sb_peer_connect.argtypes = [vp, i, vp, sz]
+    L.sb_peer_connect_local.argtypes = [vp, vp]
+    L.sb_peer_rank.argtypes = [vp]
+    L.sb_peer_world.argtypes = [vp]
+    L.sb_ctx_reserve.argtypes = [vp, i, i, sz]
+    L.sb_comm_foreach.argtypes = [vp, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz), sz, i]
     for t, ct in (("i32", C.c_int32), ("i64", C.c_int64), ("f32", C.c_float), ("f64", C.c_double)):
         getattr(L, f"sb_fill_{t}").argtypes = [vp, vp, sz, ct]
     L.sb_copy.argtypes = [vp, vp, vp, sz]
@@ -270,11 +288,45 @@ class Context:
         _check(getattr(lib(), f"sb_exclusive_carry_{t}")(self._h, _ptr(totals), rank, _ptr(out)))
         return out
 
-    def check_iota(self, data, mismatches, offset: int = 0, kind: int = 0, seg_len: int = 0, n: Optional[int] = None, dtype: Optional[str] = None):
+    def check_iota(self, data, mismatches, offset: int = 0, kind: int = 0, seg_len: int = 0, n: Optional[int] = None, dtype: Optional[str] = None,
+                   rel_tol: float = 0.0):
+        """Count elements that differ from the closed form of the iota input (integers: exactly; floating
+        point: by more than rel_tol * max(|closed form|, 1))."""
         t = dtype or dtype_of(data)
         n = data.numel() if n is None else n
-        _check(getattr(lib(), f"sb_check_iota_{t}")(self._h, _ptr(data), n, offset, kind, seg_len, _ptr(mismatches)))
+        if t[0] == "f":
+            _check(getattr(lib(), f"sb_check_iota_{t}")(self._h, _ptr(data), n, offset, kind, seg_len, rel_tol, _ptr(mismatches)))
+        else:
+            _check(getattr(lib(), f"sb_check_iota_{t}")(self._h, _ptr(data), n, offset, kind, seg_len, _ptr(mismatches)))
         return mismatches
+
+    def reserve(self, op: int, dtype: str, n: int) -> None:
+        """Pre-size the ctx scratch for `op` (0 reduce, 1 scan, 2 segreduce, 3 segscan) on n elements."""
+        _check(lib().sb_ctx_reserve(self._h, op, _DTYPE_ENUM[dtype], n))
+
+    # -- block-cyclic prefix sum (sb_scan_cyclic.cu)
+    def cyclic_block_elems(self, dtype: str) -> int:
+        return int(lib().sb_cyclic_block_elems(self._h, _DTYPE_ENUM[dtype]))
+
+    def iota_cyclic(self, out, block: int, world: int, rank: int, n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(out)
+        n = out.numel() if n is None else n
+        _check(getattr(lib(), f"sb_iota_cyclic_{t}")(self._h, _ptr(out), n, block, world, rank))
+        return out
+
+    def check_iota_cyclic(self, data, mismatches, block: int, world: int, rank: int, kind: int = 0, rel_tol: float = 0.0,
+                          n: Optional[int] = None, dtype: Optional[str] = None):
+        t = dtype or dtype_of(data)
+        n = data.numel() if n is None else n
+        _check(getattr(lib(), f"sb_check_iota_cyclic_{t}")(self._h, _ptr(data), n, block, world, rank, kind, rel_tol, _ptr(mismatches)))
+        return mismatches
+
+    def scan_cyclic(self, x, out, peer: "Optional[Peer]" = None, exclusive: bool = False, seed=None, n: Optional[int] = None, dtype: Optional[str] = None):
+        """This rank's part of the global prefix sum over block-cyclic shards (peer=None: one GPU)."""
+        t = dtype or dtype_of(x)
+        n = x.numel() if n is None else n
+        _check(getattr(lib(), f"sb_scan_cyclic_{t}")(self._h, peer._h if peer is not None else None, _ptr(x), _ptr(out), n, int(exclusive), _ptr(seed)))
+        return out
 
     # -- host-buffer (end-to-end) calls; synchronous
     def host_reduce(self, h_in, h_out, n: Optional[int] = None, dtype: Optional[str] = None):
@@ -302,6 +354,42 @@ class Context:
         return h_out
 
 
+class Peer:
+    """Mailbox of one rank of a block-cyclic scan group (sb_peer_* in include/sb_cuda.h).  One process per
+    GPU: create, exchange `handle()` bytes with every other rank (any transport), `connect` them."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, ctx: Context, rank: int, world: int):
+        self._h = C.c_void_p()
+        self._ctx = ctx
+        _check(lib().sb_peer_create(ctx._h, rank, world, C.byref(self._h)))
+        self.rank, self.world = rank, world
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(self.HANDLE_BYTES)
+        _check(lib().sb_peer_handle(self._h, buf, self.HANDLE_BYTES))
+        return buf.raw
+
+    def connect(self, peer_rank: int, handle: bytes) -> None:
+        buf = C.create_string_buffer(bytes(handle), self.HANDLE_BYTES)
+        _check(lib().sb_peer_connect(self._h, peer_rank, buf, self.HANDLE_BYTES))
+
+    def connect_local(self, other: "Peer") -> None:
+        _check(lib().sb_peer_connect_local(self._h, other._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().sb_peer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class _BorrowedContext(Context):
     """A Context whose handle belongs to an sb_comm."""
 
@@ -316,6 +404,8 @@ class Comm:
 
     REDUCE_THEN_SCAN = 0
     SCAN_THEN_CARRY = 1
+    CYCLIC = 2
+    OP_SCAN, OP_SEGREDUCE, OP_SEGSCAN = 1, 2, 3
 
     def __init__(self, ctx: Context, ngpus: int):
         self._h = C.c_void_p()
@@ -368,6 +458,20 @@ class Comm:
         os_ = self._arr(C.c_void_p, [_ptr(x) for x in outs])
         _check(lib().sb_comm_scan(self._h, _DTYPE_ENUM[t], ins, os_, ns, int(exclusive), strategy))
         return outs
+
+
+def _comm_foreach(self, op: int, shards, outs, seg_len: int, exclusive: bool = False, dtype: Optional[str] = None):
+    """Independent per-shard segmented reduction (outs in place, shards ignored) / segmented scan / group-scope
+    scan on every rank; shards are cut on segment boundaries, nothing is exchanged."""
+    t = dtype or dtype_of(outs[0])
+    ins = Comm._arr(C.c_void_p, [_ptr(x) for x in (shards if shards is not None else outs)])
+    ns = Comm._arr(C.c_size_t, [_numel(x) for x in outs])
+    os_ = Comm._arr(C.c_void_p, [_ptr(x) for x in outs])
+    _check(lib().sb_comm_foreach(self._h, op, _DTYPE_ENUM[t], ins, os_, ns, seg_len, int(exclusive)))
+    return outs
+
+
+Comm.foreach = _comm_foreach
 
 
 def _numel(x) -> int:

@@ -47,9 +47,10 @@ def test_no_cpu_fallback(pkg):
 def test_workspace_bytes(pkg):
     L = pkg.lib()
     assert L.sb_workspace_bytes(0, 1, 1 << 28) > 0
-    # scan: 64 KB tiles, one descriptor per tile + one per round (8 B for 4-byte, 16 B for 8-byte types)
-    assert L.sb_workspace_bytes(1, 1, 1 << 30) == (2 * ((1 << 30) // 16384) + 64) * 8 + 256
-    assert L.sb_workspace_bytes(1, 2, 1 << 28) == (2 * ((1 << 28) // 8192) + 64) * 16 + 256
+    # scan: an upper bound — the smallest tile any kernel uses (16 KB), one descriptor per tile + one per round
+    # (8 B for 4-byte, 16 B for 8-byte types)
+    assert L.sb_workspace_bytes(1, 1, 1 << 30) == (2 * ((1 << 30) // 4096) + 64) * 8 + 256
+    assert L.sb_workspace_bytes(1, 2, 1 << 28) == (2 * ((1 << 28) // 2048) + 64) * 16 + 256
     assert L.sb_workspace_bytes(2, 4, 1 << 29) == 0
 
 
