@@ -10,8 +10,9 @@
 // kernel round (G tiles = 148 x 72 KB = 10.4 MB): round r of rank g is block r*P + g.  Every rank runs the same
 // persistent kernel; per tile it does
 //   phase A (tile i + D): TMA bulk load (L2 policy evict_last) -> per-warp sums -> tile aggregate -> descriptor;
-//   phase B (tile i)    : TMA bulk load of the same tile again — it was read D rounds ago and is still in the
-//                         126 MB L2 (D x 10.4 MB) — scan with the tile prefix, 128-bit stores (policy evict_first).
+//   phase B (tile i)    : 128-bit loads of the same tile straight into registers — it was read D rounds ago and is
+//                         still in the 126 MB L2 (policy evict_first: last use) — scan with the tile prefix, 128-bit
+//                         stores (policy evict_first).  The smem ring carries HBM traffic only.
 // The prefix of tile (round r, rank g, position pos) is
 //      E[r]                      everything in rounds < r, on all ranks        (running sum kept by every look-back warp)
 //    + sum_{g' < g} T[r][g']     the round totals of the lower ranks           (mailbox, written by the peers)
@@ -159,6 +160,53 @@ __device__ __forceinline__ A sum_round_aggregates(const typename Desc<A>::word* 
   return sb::warp_sum<A>(lane_sum);
 }
 
+// phase B: the warp's K rows of a FULL tile, global (L2-resident) -> registers, one 128-bit load per lane and row
+template <typename A, int K>
+__device__ __forceinline__ void tile_load_l2(A (&v)[K][16 / sizeof(A)], const A* lane_ptr, int hint, unsigned long long policy) {
+  constexpr int VEC = 16 / sizeof(A);
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    uint4 r;
+    const A* p = lane_ptr + (size_t)j * (32 * VEC);
+    if(hint) asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(policy));
+    else asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    const sb::Vec<A>& t = *reinterpret_cast<const sb::Vec<A>*>(&r);
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) v[j][c] = t.v[c];
+  }
+}
+// phase A: lane-partial sum of the warp's K rows, read from the ring (two accumulators; fixed order)
+template <typename A, int K>
+__device__ __forceinline__ A tile_sum_smem(const unsigned char* warp_rows) {
+  constexpr int VEC = 16 / sizeof(A);
+  const unsigned char* sp = warp_rows + (threadIdx.x & 31) * 16;
+  A s0 = A(0), s1 = A(0);
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    const sb::Vec<A> t = *reinterpret_cast<const sb::Vec<A>*>(sp + (size_t)j * 512);
+    A r = t.v[0];
+#pragma unroll
+    for(int c = 1; c < VEC; ++c) r += t.v[c];
+    if(j & 1) s1 += r; else s0 += r;
+  }
+  return s0 + s1;
+}
+// the same for the ragged last tile, from global memory with guards
+template <typename A, int K>
+__device__ __forceinline__ A tile_sum_global(const A* in, size_t wbase, size_t n) {
+  constexpr int VEC = 16 / sizeof(A);
+  A s0 = A(0), s1 = A(0);
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    const size_t idx = wbase + (size_t)j * (32 * VEC);
+    A r = A(0);
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) r += (idx + c < n) ? in[idx + c] : A(0);
+    if(j & 1) s1 += r; else s0 += r;
+  }
+  return s0 + s1;
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------------------------
 // warps: [0, NW) workers, NW producer, NW+1 look-back (in CTA 0 also the leader that publishes the round totals; a
 // separate leader warp would make the CTA 21 warps, which ptxas rounds to 24: 80 instead of 96 registers and spills)
@@ -195,29 +243,23 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
   __syncthreads();  // the only block-wide barrier
 
   if(warp == NW) {
-    // ===== producer: every tile is loaded twice, phase A (from HBM, kept in L2) D rounds ahead of phase B (from L2) =====
+    // ===== producer: phase-A loads only (HBM -> smem ring, L2 policy evict_last); phase B re-reads the tile from L2
+    // straight into registers, so all ring stages keep HBM requests in flight =====
     if(lane != 0) return;
-    unsigned long long keep = 0, stream = 0;
+    unsigned long long keep = 0;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
-    long long q = 0;  // load sequence number: stage = q % CY_STAGES
-    auto issue = [&](long long i, unsigned long long policy) {
-      const int stage = (int)(q % CY_STAGES);
-      if(q >= CY_STAGES) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)((q / CY_STAGES) - 1) & 1u);
-      ++q;
+    for(long long i = 0; i < my_tiles; ++i) {
+      const int stage = (int)(i % CY_STAGES);
+      if(i >= CY_STAGES) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)((i / CY_STAGES) - 1) & 1u);
       const size_t base = (size_t)(pos + i * G) * C::TILE;
       const uint32_t bar = smem_u32(&full_bar[stage]);
       if(base + C::TILE <= n) {
         mbar_expect_tx(bar, C::TILE_BYTES);
-        if(hint) bulk_load_hint(smem_u32(ring) + stage * STAGE_BYTES, in + base, C::TILE_BYTES, bar, policy);
+        if(hint) bulk_load_hint(smem_u32(ring) + stage * STAGE_BYTES, in + base, C::TILE_BYTES, bar, keep);
         else bulk_load(smem_u32(ring) + stage * STAGE_BYTES, in + base, C::TILE_BYTES, bar);
       } else {
         mbar_arrive(bar);  // ragged last tile: the workers read it from global memory with guards
       }
-    };
-    for(long long it = 0; it < my_tiles + D; ++it) {
-      if(it < my_tiles) issue(it, keep);
-      if(it >= D) issue(it - D, stream);
     }
   } else if(warp == NW + 1) {
     // ===== look-back warp: tile aggregate -> descriptor; prefix = E[r] + lower ranks' totals of round r + local aggregates =====
@@ -298,63 +340,57 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
       }
     }
   } else {
-    // ===== workers =====
+    // ===== workers: per iteration  (1) issue the L2 loads of tile it-D,  (2) phase A of tile it from the ring,
+    //                               (3) phase B of tile it-D from the registers loaded in (1) =====
     unsigned long long stream = 0;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
-    long long q = 0;
     for(long long it = 0; it < my_tiles + D; ++it) {
+      const bool do_b = it >= D;
+      const long long b = it - D;
+      const size_t bbase = do_b ? (size_t)(pos + b * G) * C::TILE : 0;
+      const size_t bw = bbase + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
+      const bool bfull = bbase + C::TILE <= n;
+      A v[K][VEC];
+      unsigned hf[K];
+      if(do_b) {
+        // the tile was read D rounds ago by phase A and is still in L2: K 128-bit loads per lane, all in flight while
+        // phase A below runs (volatile asm: they are issued here, not sunk to their first use)
+        if(bfull) tile_load_l2<A, K>(v, in + bw, hint, stream);
+        else tile_load_global<A, true, K>(v, in, bw, false, n);
+      }
       if(it < my_tiles) {
-        // ---- phase A: tile -> per-warp sums
-        const int stage = (int)(q % CY_STAGES), slot = (int)(it % CY_NSLOT);
-        const uint32_t par = (uint32_t)(q / CY_STAGES) & 1u;
-        ++q;
-        const long long tile = pos + it * G;
-        const size_t base = (size_t)tile * C::TILE;
-        const size_t wbase = base + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
-        const bool full_tile = base + C::TILE <= n;
-        A v[K][VEC];
-        unsigned hf[K];
-        mbar_wait(smem_u32(&full_bar[stage]), par);
-        if(full_tile) tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
-        else tile_load_global<A, true, K>(v, in, wbase, false, n);
-        A agg;
-        bool has_head;
-        warp_reduce_rows<A, MODE_PLAIN, K>(v, hf, agg, has_head);
+        // ---- phase A: tile -> per-warp sums, streamed out of the ring with a handful of registers
+        const int stage = (int)(it % CY_STAGES), slot = (int)(it % CY_NSLOT);
+        const size_t base = (size_t)(pos + it * G) * C::TILE;
+        mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / CY_STAGES) & 1u);
+        A s;
+        if(base + C::TILE <= n) {
+          s = tile_sum_smem<A, K>(ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
+        } else {
+          s = tile_sum_global<A, K>(in, base + (size_t)warp * C::WCHUNK + (size_t)lane * VEC, n);
+        }
+        const A agg = sb::warp_sum<A>(s);
         if(lane == 0) {
           mbar_arrive(smem_u32(&empty_bar[stage]));  // warp_sum consumed every lane's smem reads
           s_wagg[slot][warp] = agg;
           mbar_arrive(smem_u32(&agg_bar[slot]));
         }
       }
-      if(it >= D) {
-        // ---- phase B: the same tile again (L2), scan with its prefix, store
-        const long long b = it - D;
-        const int stage = (int)(q % CY_STAGES), slot = (int)(b % CY_NSLOT);
-        const uint32_t par = (uint32_t)(q / CY_STAGES) & 1u;
-        ++q;
-        const long long tile = pos + b * G;
-        const size_t base = (size_t)tile * C::TILE;
-        const size_t wbase = base + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
-        const bool full_tile = base + C::TILE <= n;
-        A v[K][VEC];
-        unsigned hf[K];
-        mbar_wait(smem_u32(&full_bar[stage]), par);
-        if(full_tile) tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
-        else tile_load_global<A, true, K>(v, in, wbase, false, n);
+      if(do_b) {
+        // ---- phase B: scan the tile with its prefix, store
+        const int slot = (int)(b % CY_NSLOT);
         A carry_in[K];
         bool open[K];
         A warp_agg;
         bool warp_has_head;
         tile_pass1<A, MODE_PLAIN, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
-        __syncwarp();
-        if(lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));  // the tile lives in registers now
         mbar_wait(smem_u32(&prefix_bar[slot]), (uint32_t)(b / CY_NSLOT) & 1u);
         const A tile_prefix = s_tprefix[slot];
         A my_prefix, tile_agg;
         bool my_open, tile_has_head;
         combine_warps<A, MODE_PLAIN, NW>(s_wagg[slot], nullptr, warp, my_prefix, my_open, tile_agg, tile_has_head);
-        if(hint) tile_pass2_store<A, MODE_PLAIN, true, K, true>(v, hf, carry_in, open, my_prefix + tile_prefix, wbase, full_tile, n, out, exclusive, stream);
-        else tile_pass2_store<A, MODE_PLAIN, true, K, false>(v, hf, carry_in, open, my_prefix + tile_prefix, wbase, full_tile, n, out, exclusive);
+        if(hint) tile_pass2_store<A, MODE_PLAIN, true, K, true>(v, hf, carry_in, open, my_prefix + tile_prefix, bw, bfull, n, out, exclusive, stream);
+        else tile_pass2_store<A, MODE_PLAIN, true, K, false>(v, hf, carry_in, open, my_prefix + tile_prefix, bw, bfull, n, out, exclusive);
       }
     }
   }

@@ -109,11 +109,19 @@ def test_comm_exclusive_scan_two_gpus(pkg):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("binary,extra", [("reduction", []), ("prefixsum", []), ("prefixsum", ["--scan-strategy=scan_then_carry"])])
-def test_pattern_binaries_num_gpus(binary, extra):
+@pytest.mark.parametrize("binary,extra,rows", [
+    ("reduction", [], 4),
+    ("prefixsum", [], 4),  # default strategy: block-cyclic shards, exchange inside the kernel
+    ("prefixsum", ["--scan-strategy=reduce_then_scan"], 4),
+    ("prefixsum", ["--scan-strategy=scan_then_carry"], 4),
+    ("scan", [], 8),  # global scope through sb_comm_scan (exclusive), group scope as replicas
+    ("segmentedscan", ["--no-flags"], 4),
+    ("segmentedreduction", [], 5),  # the int16 row stays on one GPU
+])
+def test_pattern_binaries_num_gpus(binary, extra, rows):
     exe = os.path.join(ROOT, "sycl-bench_b200", "bin", binary)
     if not os.path.exists(exe):
         pytest.skip("pattern binaries not built")
-    out = subprocess.run([exe, "--size=16777216", "--num-gpus=2", "--num-runs=2", "--strict"] + extra, capture_output=True, text=True, timeout=300)
+    out = subprocess.run([exe, "--size=16777216", "--local=256", "--num-gpus=2", "--num-runs=2", "--strict"] + extra, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert out.stdout.count("Verification: PASS") == 4 and "FAIL" not in out.stdout, out.stdout
+    assert out.stdout.count("Verification: PASS") == rows and "FAIL" not in out.stdout, out.stdout

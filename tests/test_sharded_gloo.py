@@ -90,6 +90,98 @@ def test_sharded_reduce_and_prefixsum(world, dtype_name, strategy):
     assert np.array_equal(got, want_scan)
 
 
+def _worker_cyclic_and_replicas(rank, world, port, n, block, dtype_name, q):
+    """Block-cyclic prefix sum and the exchange-free replicas through ShardedOps, local ops = the oracle.
+    The oracle stands in for sb_scan_cyclic by gathering the shards over gloo and scanning the re-assembled
+    global array: what is under test is the layout arithmetic and the plumbing of sharded.py."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    from oracle import oracle as O
+
+    ge.load_package()
+    from sycl_bench_b200 import sharded
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t = {"i32": torch.int32, "i64": torch.int64, "f64": torch.float64}[dtype_name]
+    gidx = [sharded.cyclic_global_indices(n, block, world, r) for r in range(world)]
+
+    def o_scan_cyclic(x, y, exclusive):
+        parts = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(parts, x)
+        full = np.empty(n * world, dtype=x.numpy().dtype)
+        for r in range(world):
+            full[gidx[r]] = parts[r].numpy()
+        y.copy_(torch.from_numpy(O.scan(dtype_name, full, exclusive)[gidx[rank]]))
+
+    def o_scan(x, y, exclusive, seed, group_len=0):
+        y.copy_(torch.from_numpy(O.scan(dtype_name, x.numpy(), exclusive, group_len)))
+
+    ops = sharded.ShardedOps(dist, rank, world, None, o_scan, None, None, scan_cyclic=o_scan_cyclic,
+                             segreduce=lambda x, L: x.copy_(torch.from_numpy(O.segreduce(dtype_name, x.numpy(), L))),
+                             segscan=lambda x, y, L, ex: y.copy_(torch.from_numpy(O.scan(dtype_name, x.numpy(), ex, L))))
+    # input: the reference's iota over the GLOBAL index space, in the block-cyclic layout
+    x = torch.from_numpy(gidx[rank].astype(x_np := {"i32": np.int32, "i64": np.int64, "f64": np.float64}[dtype_name]))
+    y = torch.empty_like(x)
+    ops.prefixsum(x, y, None, None, strategy="cyclic")
+    cyc = y.numpy().copy()
+    # replicas: contiguous shards cut on segment boundaries
+    L = 64
+    b, e = sharded.shard_bounds(n * world, world, rank, align=L)
+    xs = torch.from_numpy(O.iota(dtype_name, e - b, b))
+    ys = torch.empty_like(xs)
+    ops.foreach_segscan(xs, ys, L)
+    segscan = ys.numpy().copy()
+    ops.foreach_group_scan(xs, ys, L, exclusive=True)
+    gscan = ys.numpy().copy()
+    ops.foreach_segreduce(xs, L)
+    try:
+        ops.foreach_segscan(xs[:-1], ys[:-1], L)
+        raised = False
+    except ValueError:
+        raised = True
+    q.put((rank, cyc, (b, e), segscan, gscan, xs.numpy().copy(), raised))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,dtype_name,n,block", [(2, "i32", 5000, 1000), (2, "i64", 2500, 1000), (3, "f64", 3000, 1000), (3, "i32", 999, 1000)])
+def test_cyclic_prefixsum_and_replicas(world, dtype_name, n, block):
+    from oracle import oracle as O
+    import __graft_entry__ as ge
+
+    ge.load_package()
+    from sycl_bench_b200.sharded import cyclic_global_index, cyclic_global_indices
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_cyclic_and_replicas, args=(r, world, port, n, block, dtype_name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = n * world
+    # the layout is a bijection onto [0, total), rank-major inside a round, and the scalar form agrees with the vector form
+    allidx = np.concatenate([cyclic_global_indices(n, block, world, r) for r in range(world)])
+    assert np.array_equal(np.sort(allidx), np.arange(total))
+    for r in range(world):
+        for i in (0, n // 2, n - 1):
+            assert cyclic_global_index(i, n, block, world, r) == cyclic_global_indices(n, block, world, r)[i]
+    want = O.scan(dtype_name, O.iota(dtype_name, total))
+    full = O.iota(dtype_name, total)
+    L = 64
+    for rank, cyc, (b, e), segscan, gscan, segred, raised in results:
+        assert np.array_equal(cyc, want[cyclic_global_indices(n, block, world, rank)])
+        assert np.array_equal(segscan, O.scan(dtype_name, full, False, L)[b:e])
+        assert np.array_equal(gscan, O.scan(dtype_name, full, True, L)[b:e])
+        assert np.array_equal(segred, O.segreduce(dtype_name, full[: total // L * L], L)[b:e]) or (e - b) % L
+        assert raised  # a shard that is not cut on a segment boundary is refused
+    assert results[0][2][0] == 0 and results[-1][2][1] == total
+
+
 def test_shard_bounds():
     import __graft_entry__ as ge
 
