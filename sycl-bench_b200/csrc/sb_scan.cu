@@ -90,6 +90,10 @@ constexpr int WS_NW_NARROW = SB_WS_NW_NARROW;
 #define SB_WS_NW_FLAGS SB_WS_NW  // worker warps of the explicit-flag instantiation
 #endif
 constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
+#ifndef SB_WS_NW_LB64
+#define SB_WS_NW_LB64 14  // 64-bit types, segmented modes with look-back: 14 + 2 = 16 warps -> 128 registers per thread
+#endif
+constexpr int WS_NW_LB64 = SB_WS_NW_LB64;
 constexpr int WS_NSLOT = 2 * WS_DEPTH + 2;  // a fast warp is at most DEPTH+1 tiles ahead of a slow one
 
 using namespace sbscan;
@@ -287,11 +291,27 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
   __shared__ A s_wagg[WS_NSLOT][NW];
   __shared__ int s_wflag[WS_NSLOT][NW];
   __shared__ A s_tprefix[WS_NSLOT];
-  __shared__ int s_first_head[WS_NSLOT];
+  __shared__ __align__(8) unsigned long long xchg_bar;  // workers' barrier of "lazy" tiles (below)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long G = gridDim.x;
   const long long my_tiles = (num_tiles - (long long)blockIdx.x + G - 1) / G;  // tiles blockIdx.x + i*G
+
+  // Segmented modes: does tile t start on a segment head?  (one flag byte, or arithmetic on the tile base)
+  auto starts_on_head = [&](long long t) -> bool {
+    if(MODE == MODE_PLAIN) return false;
+    if(t == 0) return true;  // element 0 always starts a segment
+    const size_t first = (size_t)t * C::TILE;
+    if(MODE == MODE_IMPLICIT) return seg_mask != ~(size_t)0 ? (first & seg_mask) == 0 : first % seg_len == 0;
+    return __ldg(flags + first) != 0;
+  };
+  // A tile is LAZY when the tile behind it starts on a head (or there is none): no later tile can need its aggregate
+  // — a walk back from tile j stops at the nearest tile holding a head, and tile t+1 holds one — so phase A is
+  // skipped (a dummy descriptor keeps the pollers going) and the warps exchange their sums inside phase B instead.
+  // With heads every 256 elements every tile is lazy and the kernel does one pass over the ring per tile instead
+  // of two: ncu had the explicit-flag kernel at 64 % issue-slot utilisation with 4.5 warps per scheduler, i.e.
+  // instruction-bound (profiles/r02_ncu_scan_flags.txt).
+  auto is_lazy = [&](long long t) -> bool { return MODE != MODE_PLAIN && (t + 1 >= num_tiles || starts_on_head(t + 1)); };
 
   if(threadIdx.x == 0) {
 #pragma unroll
@@ -304,6 +324,7 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
       mbar_init(smem_u32(&agg_bar[s]), NW);
       mbar_init(smem_u32(&prefix_bar[s]), 1);
     }
+    mbar_init(smem_u32(&xchg_bar), NW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();  // the only block-wide barrier
@@ -336,14 +357,19 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
     for(long long i = 0; i < my_tiles; ++i) {
       const int slot = (int)(i % WS_NSLOT);
       const long long tile = (long long)blockIdx.x + i * G;
+      const bool on_head = starts_on_head(tile), lazy = is_lazy(tile);  // (the flag-byte loads fly during the wait)
       mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(i / WS_NSLOT) & 1u);
-      A my_prefix, tile_agg;
-      bool my_open, tile_has_head;
-      combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], -1, my_prefix, my_open, tile_agg, tile_has_head);
+      A tile_agg = A(0);
+      bool tile_has_head = false;
+      if(!lazy) {
+        A my_prefix;
+        bool my_open;
+        combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], -1, my_prefix, my_open, tile_agg, tile_has_head);
+      }
+      // a lazy tile publishes a placeholder: its value is never used (see is_lazy), its presence is what pollers wait for
       if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | (tile_has_head ? ST_INCL : ST_AGG), tile_agg);
       A p = A(0);
-      const bool starts_on_head = MODE != MODE_PLAIN && s_first_head[slot];
-      if(!starts_on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed);
+      if(!on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed);
       if(lane == 0) {
         if((tile + 1) % G == 0)
           Desc<A>::store(const_cast<typename Desc<A>::word*>(rdesc) + tile / G, (epoch << 2) | ST_INCL, tile_has_head ? tile_agg : p + tile_agg);
@@ -391,29 +417,40 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
       return;
     }
     // ===== workers: phase A runs WS_DEPTH tiles ahead of phase B =====
+    unsigned lazy_hist = 0;   // bit d: tile (it - d) of this CTA is lazy
+    unsigned lazy_done = 0;   // lazy tiles finished so far: phase of xchg_bar
+    bool lazy_nxt = my_tiles > 0 && is_lazy((long long)blockIdx.x);
     for(long long it = 0; it < my_tiles + WS_DEPTH; ++it) {
+      lazy_hist <<= 1;
+      // the decision for the NEXT tile is requested one iteration ahead: with explicit flags it is a global load
+      const bool lazy_cur = lazy_nxt;
+      lazy_nxt = it + 1 < my_tiles && is_lazy((long long)blockIdx.x + (it + 1) * G);
       if(it < my_tiles) {
         // ---- phase A: tile -> per-warp (sum, has-head) for the look-back warp
         const int stage = (int)(it % WS_STAGES), slot = (int)(it % WS_NSLOT);
         const long long tile = (long long)blockIdx.x + it * G;
-        const size_t wbase = (size_t)tile * C::TILE + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
-        const bool full_tile = (size_t)(tile + 1) * C::TILE <= n;
-        A v[K][VEC];
-        unsigned hf[K];
-        const bool ring_flags = MODE == MODE_FLAGS && flags_in_ring && full_tile;
-        if(!ring_flags) tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);  // flag loads fly while we wait
-        mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / WS_STAGES) & 1u);
-        if(ring_flags) tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
-        if(full_tile) tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
-        else tile_load_global<A, true, K>(v, in, wbase, false, n);  // ragged last tile
-        A agg;
-        bool has_head;
-        warp_reduce_rows<A, MODE, K>(v, hf, agg, has_head);
-        if(lane == 0) {
-          s_wagg[slot][warp] = agg;
-          s_wflag[slot][warp] = has_head ? 1 : 0;
-          if(warp == 0) s_first_head[slot] = (int)(hf[0] & 1u);
-          mbar_arrive(smem_u32(&agg_bar[slot]));
+        if(lazy_cur) {
+          lazy_hist |= 1u;
+          if(lane == 0) mbar_arrive(smem_u32(&agg_bar[slot]));  // nothing to contribute: wakes the look-back warp
+        } else {
+          const size_t wbase = (size_t)tile * C::TILE + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
+          const bool full_tile = (size_t)(tile + 1) * C::TILE <= n;
+          A v[K][VEC];
+          unsigned hf[K];
+          const bool ring_flags = MODE == MODE_FLAGS && flags_in_ring && full_tile;
+          if(!ring_flags) tile_head_flags<A, MODE, K>(hf, wbase, n, seg_len, seg_mask, flags);  // flag loads fly while we wait
+          mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / WS_STAGES) & 1u);
+          if(ring_flags) tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
+          if(full_tile) tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
+          else tile_load_global<A, true, K>(v, in, wbase, false, n);  // ragged last tile
+          A agg;
+          bool has_head;
+          warp_reduce_rows<A, MODE, K>(v, hf, agg, has_head);
+          if(lane == 0) {
+            s_wagg[slot][warp] = agg;
+            s_wflag[slot][warp] = has_head ? 1 : 0;
+            mbar_arrive(smem_u32(&agg_bar[slot]));
+          }
         }
       }
       if(it >= WS_DEPTH) {
@@ -424,8 +461,10 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         const size_t base = (size_t)tile * C::TILE;
         const size_t wbase = base + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
         const bool full_tile = base + C::TILE <= n;
+        const bool lazy = (lazy_hist >> WS_DEPTH) & 1u;
         A v[K][VEC];
         unsigned hf[K];
+        if(lazy) mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(b / WS_STAGES) & 1u);  // phase A did not wait for the data
         if(MODE == MODE_FLAGS && flags_in_ring && full_tile)
           tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
         else
@@ -442,7 +481,17 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         // ~45 % of the warp samples in mbarrier wait loops with one 64 KB stage in flight per SM at most.
         __syncwarp();
         if(lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
-        // all warps' phase-A pairs of this tile (and, with look-back, the tile prefix) are complete
+        if(lazy) {
+          // the warp sums phase A did not produce: exchange them now (one barrier among the workers)
+          if(lane == 0) {
+            s_wagg[slot][warp] = warp_agg;
+            s_wflag[slot][warp] = warp_has_head ? 1 : 0;
+            mbar_arrive(smem_u32(&xchg_bar));
+          }
+          mbar_wait(smem_u32(&xchg_bar), lazy_done & 1u);
+          ++lazy_done;
+        }
+        // all warps' pairs of this tile (and, with look-back, the tile prefix) are complete
         const uint32_t par = (uint32_t)(b / WS_NSLOT) & 1u;
         A tile_prefix = A(0);
         if(use_lookback) {
@@ -640,8 +689,13 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   // warps ptxas has 96 and spills (fp64 group scan 5.5 -> 6.4 TB/s)
   constexpr size_t narrow_tile = TileCfg<A, WS_NW_NARROW, WS_K>::TILE;
   const bool narrow = mode == MODE_IMPLICIT && sizeof(A) == 8 && sb::is_pow2(seg_len) && narrow_tile % seg_len == 0;
-  const size_t ws_tile = mode == MODE_FLAGS ? TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS>::K>::TILE
-                         : wide ? wide_tile : narrow ? narrow_tile : TileCfg<A, WS_NW, WS_K>::TILE;
+  // 64-bit types on the look-back kernel in a segmented mode: 14 workers + producer + look-back = 16 warps, so that a
+  // thread may use 128 registers (at 18 warps ptxas has 96 and spills 100-270 bytes, profiles/r02_ptxas_spills.txt).
+  // SB_SCAN_LB64_NW=16 keeps the 16-worker instantiation (A/B measurements).
+  static const bool lb64_enabled = !(getenv("SB_SCAN_LB64_NW") && atoi(getenv("SB_SCAN_LB64_NW")) == 16);
+  const bool lb64 = lb64_enabled && sizeof(A) == 8 && (mode == MODE_FLAGS || (mode == MODE_IMPLICIT && !narrow));
+  const size_t ws_tile = mode == MODE_FLAGS ? (lb64 ? TileCfg<A, WS_NW_LB64, ws_rows<MODE_FLAGS>::K>::TILE : TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS>::K>::TILE)
+                         : wide ? wide_tile : narrow ? narrow_tile : lb64 ? TileCfg<A, WS_NW_LB64, WS_K>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
   const size_t simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
   const bool use_ws = aligned && n >= 4 * ws_tile;
   const size_t tile = use_ws ? ws_tile : simple_tile;
@@ -680,7 +734,9 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
     if(mode == MODE_PLAIN) rc = launch_ws<A, MODE_PLAIN, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && wide) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && narrow) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_NARROW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else if(mode == MODE_IMPLICIT && lb64) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT) rc = launch_ws<A, MODE_IMPLICIT, WS_NW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     if(rc != SB_OK) return rc;
     SB_CHECK_LAUNCH(ctx);

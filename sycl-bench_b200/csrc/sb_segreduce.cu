@@ -19,12 +19,17 @@
 //  - segments longer than a super-row accumulate in registers over their super-rows first;
 //  - grid = sm_count x 8 CTAs of 256 threads, warp-granular grid-stride: a CTA reads 16 KB
 //    contiguous per iteration.
+//  - large inputs (>= 4 tiles of 64 KB) with segments of at most a super-row go through segreduce_ring_kernel: the
+//    same per-segment arithmetic, but the rows arrive through a persistent cp.async.bulk (TMA) ring, tiles handed out
+//    in order by an atomic ticket: 192 KB in flight per SM regardless of registers and occupancy.  ncu on the
+//    register-fed kernel at L=64 (profiles/r02_ncu_segreduce_L64.txt): 47-54 % warps active, 22-26 % issue active,
+//    28 long-scoreboard cycles per instruction — latency-bound with too few bytes in flight.
 // A generic warp-per-segment kernel covers everything else (L not a power of two, L < 16 B,
 // unaligned buffers); it sums exactly the subset of a segment the reference's halving tree
 // reaches (oracle/sb_oracle.c: ref_tree_member).
 #include <cstdlib>
 
-#include "sb_common.cuh"
+#include "sb_scan_tile.cuh"
 
 namespace {
 
@@ -170,6 +175,88 @@ __global__ void __launch_bounds__(NT) segreduce_rows_kernel(A* buf, size_t n) {
   }
 }
 
+// ---- the same arithmetic fed by a TMA ring (large inputs) ----------------------------------------------------------
+// warps [0, SRR_NW): workers, each owns 8 consecutive rows (two super-rows) of a tile; warp SRR_NW: producer.
+constexpr int SRR_NW = 16, SRR_STAGES = 3, SRR_TILE_BYTES = SRR_NW * 8 * 512, SRR_IDS = 8;
+
+template <typename A, int SHAPE>
+__global__ void __launch_bounds__((SRR_NW + 1) * 32, 1)
+segreduce_ring_kernel(A* buf, size_t n, long long num_tiles, unsigned long long* ticket, unsigned long long ticket_base) {
+  using namespace sbscan;
+  constexpr int VEC = 16 / sizeof(A);
+  constexpr size_t ROW = 32 * VEC, SUPER = 4 * ROW, TILE = SRR_TILE_BYTES / sizeof(A);
+  extern __shared__ __align__(128) unsigned char ring[];  // SRR_STAGES x SRR_TILE_BYTES
+  __shared__ __align__(8) unsigned long long full_bar[SRR_STAGES], empty_bar[SRR_STAGES];
+  __shared__ long long s_tile_id[SRR_IDS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if(threadIdx.x == 0) {
+#pragma unroll
+    for(int s = 0; s < SRR_STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), SRR_NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if(warp == SRR_NW) {
+    if(lane != 0) return;
+    for(int i = 0;; ++i) {
+      const int stage = i % SRR_STAGES;
+      if(i >= SRR_STAGES) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)((i / SRR_STAGES) - 1) & 1u);
+      const long long tile = (long long)(atomicAdd(ticket, 1ull) - ticket_base);
+      const uint32_t bar = smem_u32(&full_bar[stage]);
+      if(tile >= num_tiles) {
+        s_tile_id[i % SRR_IDS] = -1;
+        mbar_arrive(bar);  // releases the workers; they read the -1 and leave
+        break;
+      }
+      s_tile_id[i % SRR_IDS] = tile;
+      const size_t base = (size_t)tile * TILE;
+      if(base + TILE <= n) {
+        mbar_expect_tx(bar, SRR_TILE_BYTES);
+        bulk_load(smem_u32(ring) + stage * SRR_TILE_BYTES, buf + base, SRR_TILE_BYTES, bar);
+      } else {
+        mbar_arrive(bar);  // ragged last tile: read from global memory by the workers
+      }
+    }
+    return;
+  }
+  for(int it = 0;; ++it) {
+    const int stage = it % SRR_STAGES;
+    mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / SRR_STAGES) & 1u);
+    const long long tile = s_tile_id[it % SRR_IDS];
+    if(tile < 0) break;
+    const size_t base = (size_t)tile * TILE + (size_t)warp * 2 * SUPER;  // first element of the warp's two super-rows
+    if((size_t)(tile + 1) * TILE <= n) {
+      sb::Vec<A> t0[4], t1[4];
+      const unsigned char* sp = ring + (size_t)stage * SRR_TILE_BYTES + (size_t)warp * 8 * 512 + lane * 16;
+#pragma unroll
+      for(int u = 0; u < 4; ++u) {
+        t0[u] = *reinterpret_cast<const sb::Vec<A>*>(sp + u * 512);
+        t1[u] = *reinterpret_cast<const sb::Vec<A>*>(sp + (4 + u) * 512);
+      }
+      __syncwarp();
+      if(lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));  // the rows live in registers now
+      reduce_superrow<A, SHAPE, false>(t0, buf + base, lane, 4);
+      reduce_superrow<A, SHAPE, false>(t1, buf + base + SUPER, lane, 4);
+    } else {
+      if(lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));
+      // ragged last tile (n is a multiple of the row length): whole rows remain, read with guards from global memory
+#pragma unroll
+      for(int h = 0; h < 2; ++h) {
+        const size_t b = base + h * SUPER;
+        if(b < n) {
+          const size_t rows = (n - b) / ROW;
+          const int valid_rows = rows < 4 ? (int)rows : 4;
+          sb::Vec<A> t[4];
+          load_superrow<A, true>(t, buf + b, lane, valid_rows);
+          reduce_superrow<A, SHAPE, true>(t, buf + b, lane, valid_rows);
+        }
+      }
+    }
+  }
+}
+
 // rows of a partial super-row may themselves be partial when a segment is shorter than a row:
 // such tails are left to the generic kernel (see segreduce_impl: the row kernel gets a multiple of ROW)
 
@@ -232,8 +319,33 @@ __global__ void __launch_bounds__(NT) segreduce_generic_kernel(A* buf, size_t n,
   }
 }
 
+// SB_SEGREDUCE_RING=0 keeps the register-fed kernel for every size (A/B measurements)
+inline bool ring_enabled() {
+  static const bool on = !(getenv("SB_SEGREDUCE_RING") && getenv("SB_SEGREDUCE_RING")[0] == '0');
+  return on;
+}
+
 template <typename A, int SHAPE>
 void launch_rows(sb_ctx* ctx, A* buf, size_t n, size_t blocks) {
+  constexpr size_t TILE = SRR_TILE_BYTES / sizeof(A);
+  const size_t tiles = (n + TILE - 1) / TILE;
+  if(ring_enabled() && tiles >= 4) {
+    constexpr size_t smem = (size_t)SRR_STAGES * SRR_TILE_BYTES;
+    static bool configured[64] = {};
+    if(ctx->device >= 0 && ctx->device < 64 && !configured[ctx->device]) {
+      if(cudaFuncSetAttribute(segreduce_ring_kernel<A, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) configured[ctx->device] = true;
+      (void)cudaGetLastError();
+    }
+    if(ctx->device >= 0 && ctx->device < 64 && configured[ctx->device]) {
+      size_t grid = (size_t)ctx->sm_count;
+      if(grid > tiles) grid = tiles;
+      // every CTA's producer draws tickets until one is past the last tile: tiles + grid tickets per launch
+      const unsigned long long tbase = ctx->scan_ticket_base;
+      segreduce_ring_kernel<A, SHAPE><<<(unsigned)grid, (SRR_NW + 1) * 32, smem, ctx->stream>>>(buf, n, (long long)tiles, ctx->scan_ticket, tbase);
+      if(cudaPeekAtLastError() == cudaSuccess) ctx->scan_ticket_base += tiles + grid;
+      return;
+    }
+  }
   segreduce_rows_kernel<A, SR_NT, SHAPE><<<(unsigned)blocks, SR_NT, 0, ctx->stream>>>(buf, n);
 }
 

@@ -21,7 +21,15 @@ protected:
   BenchmarkArgs _args;
   PrefetchedBuffer<T> _in, _out;
 
-  static std::size_t count(const BenchmarkArgs& a) { return a.problem_size * a.problem_size * a.problem_size / sizeof(T); }
+  // elements of the buffer, computed like upstream's getBufferSize per dimensionality (:11-22): the integer division
+  // by sizeof(T) happens at a different place for 1, 2 and 3 dimensions, which matters when --size is not a
+  // multiple of sizeof(T) (--size=10, fp32: 250 / 250 / 200 elements)
+  static std::size_t count(const BenchmarkArgs& a) {
+    const std::size_t p = a.problem_size;
+    if(Dims == 1) return p * p * p / sizeof(T);
+    if(Dims == 2) return (p * p / sizeof(T)) * p;
+    return (p / sizeof(T)) * p * p;
+  }
 
 public:
   MicroBenchDRAM(const BenchmarkArgs& args) : _args{args} {}

@@ -243,6 +243,23 @@ def test_segreduce_vs_oracle(ctx, O, t, L):
 
 
 @pytest.mark.parametrize("t", ["i16", "i32", "i64", "f32", "f64"])
+@pytest.mark.parametrize("L", [8, 16, 32, 64, 128, 256, 512, 1024])
+def test_segreduce_ring_kernel_sizes(ctx, O, t, L):
+    """Inputs of several 64 KB tiles take the TMA-ring kernel: full tiles, a ragged last tile, a tail shorter than
+    a row; random input (the heads are sums of +-2^15 values)."""
+    size = {"i16": 2, "i32": 4, "i64": 8, "f32": 4, "f64": 8}[t]
+    if L * size < 16:
+        pytest.skip("segments below 16 bytes take the generic kernel")
+    tile = 65536 // size
+    for n in (4 * tile, 5 * tile + 3 * (512 // size), (7 * tile + tile // 2 + 13 * L) // L * L):
+        n = n // L * L
+        hx = rand_input(t, n, seed=L)
+        x = dev(hx)
+        ctx.segreduce(x, L)
+        assert_close(t, x.cpu().numpy(), O.segreduce(t, hx, L), n, f"ring segreduce L={L} n={n}")
+
+
+@pytest.mark.parametrize("t", ["i16", "i32", "i64", "f32", "f64"])
 def test_segreduce_random_and_unaligned(ctx, O, t):
     L, n = 256, 256 * 999
     hx = rand_input(t, n + 1)
