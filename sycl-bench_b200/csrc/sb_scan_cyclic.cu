@@ -10,9 +10,10 @@
 // kernel round (G tiles = 148 x 72 KB = 10.4 MB): round r of rank g is block r*P + g.  Every rank runs the same
 // persistent kernel; per tile it does
 //   phase A (tile i + D): TMA bulk load (L2 policy evict_last) -> per-warp sums -> tile aggregate -> descriptor;
-//   phase B (tile i)    : 128-bit loads of the same tile straight into registers — it was read D rounds ago and is
-//                         still in the 126 MB L2 (policy evict_first: last use) — scan with the tile prefix, 128-bit
-//                         stores (policy evict_first).  The smem ring carries HBM traffic only.
+//   phase B (tile i)    : TMA bulk load of the same tile again — it was read D rounds ago and is still in the
+//                         126 MB L2 (policy evict_first: last use) — scan with the tile prefix, 128-bit stores
+//                         (policy evict_first).  The two kinds of load alternate in one smem ring, so the distance
+//                         between the two reads of a tile is exactly D rounds (D x 10.4 MB of L2).
 // The prefix of tile (round r, rank g, position pos) is
 //      E[r]                      everything in rounds < r, on all ranks        (running sum kept by every look-back warp)
 //    + sum_{g' < g} T[r][g']     the round totals of the lower ranks           (mailbox, written by the peers)
@@ -43,6 +44,14 @@
 #endif
 #ifndef SB_CY_STAGES
 #define SB_CY_STAGES 3
+#endif
+// phase B source: 0 = second TMA load of the tile through the smem ring, interleaved with the phase-A loads (the
+// distance between the two reads of a tile is exactly D rounds); 1 = 128-bit loads straight into registers, the ring
+// carrying phase-A loads only.  Measured (profiles/r02_cyclic_variants.txt): variant 1 keeps more HBM requests in
+// flight but the ring's own look-ahead (3 tiles) adds to the distance — at D=2 40 % of the re-reads miss L2
+// (dram read 3.0 GB for 2.15) and the kernel drops from 5.9 to 4.8 TB/s.  Default 0.
+#ifndef SB_CY_BLOAD
+#define SB_CY_BLOAD 0
 #endif
 
 constexpr int CY_MAX_WORLD = 16;
@@ -243,23 +252,30 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
   __syncthreads();  // the only block-wide barrier
 
   if(warp == NW) {
-    // ===== producer: phase-A loads only (HBM -> smem ring, L2 policy evict_last); phase B re-reads the tile from L2
-    // straight into registers, so all ring stages keep HBM requests in flight =====
+    // ===== producer: phase-A loads (HBM, L2 policy evict_last) and, interleaved D rounds behind them, the phase-B
+    // loads of the same tiles (L2 hits, policy evict_first: last use) =====
     if(lane != 0) return;
-    unsigned long long keep = 0;
+    unsigned long long keep = 0, stream = 0;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-    for(long long i = 0; i < my_tiles; ++i) {
-      const int stage = (int)(i % CY_STAGES);
-      if(i >= CY_STAGES) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)((i / CY_STAGES) - 1) & 1u);
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
+    long long q = 0;  // load sequence number: stage = q % CY_STAGES
+    auto issue = [&](long long i, unsigned long long policy) {
+      const int stage = (int)(q % CY_STAGES);
+      if(q >= CY_STAGES) mbar_wait(smem_u32(&empty_bar[stage]), (uint32_t)((q / CY_STAGES) - 1) & 1u);
+      ++q;
       const size_t base = (size_t)(pos + i * G) * C::TILE;
       const uint32_t bar = smem_u32(&full_bar[stage]);
       if(base + C::TILE <= n) {
         mbar_expect_tx(bar, C::TILE_BYTES);
-        if(hint) bulk_load_hint(smem_u32(ring) + stage * STAGE_BYTES, in + base, C::TILE_BYTES, bar, keep);
+        if(hint) bulk_load_hint(smem_u32(ring) + stage * STAGE_BYTES, in + base, C::TILE_BYTES, bar, policy);
         else bulk_load(smem_u32(ring) + stage * STAGE_BYTES, in + base, C::TILE_BYTES, bar);
       } else {
         mbar_arrive(bar);  // ragged last tile: the workers read it from global memory with guards
       }
+    };
+    for(long long it = 0; it < my_tiles + D; ++it) {
+      if(it < my_tiles) issue(it, keep);
+      if(SB_CY_BLOAD == 0 && it >= D) issue(it - D, stream);
     }
   } else if(warp == NW + 1) {
     // ===== look-back warp: tile aggregate -> descriptor; prefix = E[r] + lower ranks' totals of round r + local aggregates =====
@@ -340,10 +356,10 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
       }
     }
   } else {
-    // ===== workers: per iteration  (1) issue the L2 loads of tile it-D,  (2) phase A of tile it from the ring,
-    //                               (3) phase B of tile it-D from the registers loaded in (1) =====
+    // ===== workers: per iteration phase A of tile `it` (from the ring), then phase B of tile it-D =====
     unsigned long long stream = 0;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
+    long long q = 0;  // ring sequence number, in step with the producer
     for(long long it = 0; it < my_tiles + D; ++it) {
       const bool do_b = it >= D;
       const long long b = it - D;
@@ -352,17 +368,18 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
       const bool bfull = bbase + C::TILE <= n;
       A v[K][VEC];
       unsigned hf[K];
-      if(do_b) {
-        // the tile was read D rounds ago by phase A and is still in L2: K 128-bit loads per lane, all in flight while
-        // phase A below runs (volatile asm: they are issued here, not sunk to their first use)
+      if(SB_CY_BLOAD == 1 && do_b) {
+        // variant 1: the K 128-bit loads per lane are in flight while phase A below runs (volatile asm: issued here)
         if(bfull) tile_load_l2<A, K>(v, in + bw, hint, stream);
         else tile_load_global<A, true, K>(v, in, bw, false, n);
       }
       if(it < my_tiles) {
         // ---- phase A: tile -> per-warp sums, streamed out of the ring with a handful of registers
-        const int stage = (int)(it % CY_STAGES), slot = (int)(it % CY_NSLOT);
+        const int stage = (int)(q % CY_STAGES), slot = (int)(it % CY_NSLOT);
+        const uint32_t par = (uint32_t)(q / CY_STAGES) & 1u;
+        ++q;
         const size_t base = (size_t)(pos + it * G) * C::TILE;
-        mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(it / CY_STAGES) & 1u);
+        mbar_wait(smem_u32(&full_bar[stage]), par);
         A s;
         if(base + C::TILE <= n) {
           s = tile_sum_smem<A, K>(ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
@@ -377,13 +394,25 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
         }
       }
       if(do_b) {
-        // ---- phase B: scan the tile with its prefix, store
+        // ---- phase B: the same tile again, scan with its prefix, store
         const int slot = (int)(b % CY_NSLOT);
+        if(SB_CY_BLOAD == 0) {
+          const int stage = (int)(q % CY_STAGES);
+          const uint32_t par = (uint32_t)(q / CY_STAGES) & 1u;
+          ++q;
+          mbar_wait(smem_u32(&full_bar[stage]), par);
+          if(bfull) tile_load_smem<A, K>(v, ring + (size_t)stage * STAGE_BYTES + (size_t)warp * K * 512);
+          else tile_load_global<A, true, K>(v, in, bw, false, n);
+        }
         A carry_in[K];
         bool open[K];
         A warp_agg;
         bool warp_has_head;
         tile_pass1<A, MODE_PLAIN, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+        if(SB_CY_BLOAD == 0) {
+          __syncwarp();
+          if(lane == 0) mbar_arrive(smem_u32(&empty_bar[(int)((q - 1) % CY_STAGES)]));  // the tile lives in registers now
+        }
         mbar_wait(smem_u32(&prefix_bar[slot]), (uint32_t)(b / CY_NSLOT) & 1u);
         const A tile_prefix = s_tprefix[slot];
         A my_prefix, tile_agg;
