@@ -311,7 +311,9 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
   // With heads every 256 elements every tile is lazy and the kernel does one pass over the ring per tile instead
   // of two: ncu had the explicit-flag kernel at 64 % issue-slot utilisation with 4.5 warps per scheduler, i.e.
   // instruction-bound (profiles/r02_ncu_scan_flags.txt).
-  auto is_lazy = [&](long long t) -> bool { return MODE != MODE_PLAIN && (t + 1 >= num_tiles || starts_on_head(t + 1)); };
+  // Explicit flags only: there phase A is as expensive as pass 1 (chained per-row reductions).  With implicit heads
+  // phase A is cheap and the extra barrier in phase B costs more than it saves (L=65536: 4.5 -> 3.8 TB/s measured).
+  auto is_lazy = [&](long long t) -> bool { return MODE == MODE_FLAGS && (t + 1 >= num_tiles || starts_on_head(t + 1)); };
 
   if(threadIdx.x == 0) {
 #pragma unroll

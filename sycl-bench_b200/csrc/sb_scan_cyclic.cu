@@ -504,7 +504,7 @@ int scan_cyclic_impl(sb_ctx* ctx, sb_peer* peer, const T* in, T* out, size_t n, 
   }
   // look-ahead in rounds and L2 policies: defaults from the measurements in profiles/ (r02); the env knobs exist for tuning runs
   static const int env_depth = env_int("SB_CYCLIC_DEPTH", 0, 0, CY_MAX_DEPTH), env_hint = env_int("SB_CYCLIC_HINT", -1, -1, 1);
-  int D = env_depth > 0 ? env_depth : (peer->world > 1 ? 4 : 2);
+  int D = env_depth > 0 ? env_depth : (peer->world > 1 ? 3 : 2);  // rounds of 10.4 MB: L2 keeps ~3 of them (profiles/r02_cyclic_variants.txt)
   int hint = env_hint >= 0 ? env_hint : 1;
   size_t grid = (size_t)G < tiles ? (size_t)G : tiles;
   const A* ain = reinterpret_cast<const A*>(in);

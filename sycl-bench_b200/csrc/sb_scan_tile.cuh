@@ -298,8 +298,12 @@ __device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], cons
       tile_pass1<A, MODE_PLAIN, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
       return;
     }
+#ifndef SB_SCAN_UNCHAINED
+    // (SB_SCAN_UNCHAINED: fall through to the K independent row scans below also when the chunk holds heads —
+    // ILP K instead of K dependent shuffle chains, at the price of the per-row totals / head masks in registers)
     tile_pass1_chained<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
     return;
+#endif
   }
   constexpr int VEC = 16 / sizeof(A);
   const int lane = threadIdx.x & 31;
