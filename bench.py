@@ -337,9 +337,13 @@ class Bench:
         types = sorted({t for _, t, _ in legs})
         x = {t: self.empty(t, n) for t in types}
         y = {t: self.empty(t, n) for t in types}
+        # the block-cyclic layout belongs to the global reduce / prefix-sum legs; replicas own contiguous shards
+        replicas = any(op in ("gscan", "segscan", "segreduce") for op, _, _ in legs)
         for t in types:
             if solo:
                 self.ctx.iota(x[t], offset=0)
+            elif replicas:
+                self.ctx.iota(x[t], offset=self.rank * n)
             else:
                 self.fill_input(x[t], t, n)
             if any(op == "segreduce" for op, tt, _ in legs if tt == t):

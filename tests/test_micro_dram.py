@@ -56,3 +56,36 @@ def test_dram_binary_rows(tmp_path):
     for row in rows.values():
         assert row["Verification"] == "PASS" and row["kernel-launches-per-run"] == "1"
         assert abs(float(row["throughput-metric"]) - 2 * 256**3 / 2**30) < 1e-9  # 2 x buffer GiB, DRAM.cpp:45-50
+
+
+@pytest.mark.gpu
+def test_gpu_copy_rejects_partial_overlap(ctx, pkg):
+    """The copy kernel reads through the read-only path: overlapping ranges are refused (dst == src is a no-op)."""
+    import torch
+
+    buf = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    with pytest.raises(pkg.SbError) as e:
+        ctx.copy(buf[16:], buf, 1024)
+    assert e.value.status == -1
+    with pytest.raises(pkg.SbError):
+        ctx.copy(buf, buf[1000:], 1024)
+    ctx.copy(buf, buf, 1024)
+    ctx.copy(buf[2048:], buf, 1024)  # disjoint halves are fine
+
+
+@pytest.mark.gpu
+def test_dram_element_count_follows_upstream_per_dims(tmp_path):
+    """--size=10: upstream's getBufferSize divides by sizeof(T) at a different place per dimensionality
+    (/root/reference/micro/DRAM.cpp:11-22): 250 / 250 / 200 fp32 elements, 125 / 120 / 100 fp64 elements."""
+    from oracle import oracle as O
+
+    out = tmp_path / "dram10.csv"
+    r = subprocess.run([os.path.join(BIN, "DRAM"), "--size=10", "--num-runs=1", f"--output={out}"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    rows = O.parse_csv(str(out))
+    want = {"fp32": (250, 250, 200), "fp64": (125, 120, 100)}
+    for t, size in (("fp32", 4), ("fp64", 8)):
+        for d in (1, 2, 3):
+            row = rows[f"MicroBench_DRAM_{t}_{d}"]
+            assert row["Verification"] == "PASS"
+            assert abs(float(row["throughput-metric"]) - 2 * want[t][d - 1] * size / 2**30) < 1e-12
