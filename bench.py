@@ -13,7 +13,8 @@ Metric: effective HBM GB/s = algorithmic bytes (reduce N*s + s, 
 H2D and D2H copies inside the timed region (N=1: sb_host_reduce / sb_host_scan of the C ABI; N>1: host
 shard -> device -> the SHARDED global operation -> host).
 
-N > 1 (torchrun, one rank per GPU).  reduction = local sb_reduce + NCCL all-reduce of one element.
+N > 1 (torchrun, one rank per GPU).  reduction = sb_reduce_all: the all-reduce of the per-GPU sums is the tail of the
+reduce kernel itself (peer-memory mailboxes over NVLink); --reduce-exchange nccl = sb_reduce + NCCL all-reduce of one element.
 Prefix sum, --scan-strategy:
     cyclic (default)   block-cyclic shards, sb_scan_cyclic: the round totals cross NVLink inside the kernel
                        (peer-memory mailboxes), every element is read from HBM once (2*N*s/P per GPU)
@@ -199,17 +200,19 @@ class Bench:
         self.strategy = args.scan_strategy if self.world > 1 else "single"
         self.strategy_note = None
         self.peer = None
-        if self.strategy == "cyclic":
+        if self.strategy == "cyclic" or (self.world > 1 and args.reduce_exchange == "fused"):
             try:
                 self.peer = sharded.make_peer_group(self.ctx, dist, self.rank, self.world)
                 ok = 1
             except self.pkg.SbError as e:
-                ok, self.strategy_note = 0, f"peer memory unavailable on this box ({e}); fell back to reduce_then_scan"
+                ok, self.strategy_note = 0, f"peer memory unavailable on this box ({e}); fell back to reduce_then_scan / NCCL"
             okt = torch.tensor([ok], dtype=torch.int64, device=self.dev)
             dist.all_reduce(okt, op=dist.ReduceOp.MIN)
             if int(okt.item()) == 0:
-                self.strategy, self.peer = "reduce_then_scan", None
-                self.strategy_note = self.strategy_note or "a peer rank could not map the mailboxes; fell back to reduce_then_scan"
+                self.peer = None
+                if self.strategy == "cyclic":
+                    self.strategy = "reduce_then_scan"
+                self.strategy_note = self.strategy_note or "a peer rank could not map the mailboxes; fell back to reduce_then_scan / NCCL"
         self.ops = sharded.for_context(self.ctx, dist, self.rank, self.world, peer=self.peer)
         self.tdt = {"f32": torch.float32, "i64": torch.int64, "i32": torch.int32, "f64": torch.float64}
 
@@ -274,7 +277,7 @@ class Bench:
                 if solo:
                     ctx.reduce(x, red)
                 else:
-                    self.ops.reduce(x, red)  # N>1: + ncclSum all-reduce of one element per rank
+                    self.ops.reduce(x, red, exchange=self.args.reduce_exchange)  # N>1: all-reduce inside the kernel (peer mailboxes) or NCCL
 
             def verify():
                 exact = ntot * (ntot - 1) // 2
@@ -443,7 +446,7 @@ def run_ours(args):
         "reduce_then_scan": "reduce_kernel<%s> + NCCL all-gather + seeded scan_ws_kernel (sb_reduce_%s -> sb_scan)",
         "scan_then_carry": "scan_ws_kernel<%s> + NCCL all-gather + carry_add_kernel (sb_scan_%s -> sb_carry_add)",
     }
-    kern = {"scan": kernels[B.strategy], "reduce": "reduce_kernel<%s, 512, 4> (sb_reduce_%s)" + ("" if world == 1 else " + NCCL all-reduce of one element"),
+    kern = {"scan": kernels[B.strategy], "reduce": "reduce_kernel<%s, 512, 4> (sb_reduce_%s)" + ("" if world == 1 else (" with the all-reduce fused into its last block (peer mailboxes over NVLink)" if (B.peer is not None and args.reduce_exchange == "fused") else " + NCCL all-reduce of one element")),
             "gscan": "scan_independent_kernel<%s> (sb_scan_%s, group scope)", "segscan": "scan_independent_kernel<%s> (sb_segscan_%s)",
             "segreduce": "segreduce_rows_kernel<%s> (sb_segreduce_%s)"}[dom[0]] % (dom[1], dom[1])
     roofline = {"bound": "hbm", "kernel": kern, "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -476,17 +479,18 @@ def run_ours(args):
         cpu = cpu_reference(legs, sample_log2=args.cpu_log2n, steps=1, warmup=1, budget_s=40.0)["cpu_baseline"]
 
     if rank == 0:
+        red = "sb_reduce_all (all-reduce inside the kernel, peer mailboxes)" if (B.peer is not None and args.reduce_exchange == "fused") else "sb_reduce + NCCL all-reduce(1 elt)"
         par = {"single": "1 GPU",
-               "cyclic": f"{world} GPUs, block-cyclic shards (block = {B.ctx.sm_count} tiles of 72 KB); reduce: local + NCCL all-reduce(1 elt); prefixsum: sb_scan_cyclic, round totals over NVLink peer memory inside the kernel, 2 passes",
-               "reduce_then_scan": f"{world} contiguous shards; reduce: NCCL all-reduce(1 elt); prefixsum: sb_reduce -> NCCL all-gather -> seeded sb_scan, 3 passes",
-               "scan_then_carry": f"{world} contiguous shards; reduce: NCCL all-reduce(1 elt); prefixsum: sb_scan -> NCCL all-gather -> sb_carry_add, 4 passes"}[B.strategy]
+               "cyclic": f"{world} GPUs, block-cyclic shards (block = {B.ctx.sm_count} tiles of 72 KB); reduce: {red}; prefixsum: sb_scan_cyclic, round totals over NVLink peer memory inside the kernel, 2 passes",
+               "reduce_then_scan": f"{world} contiguous shards; reduce: {red}; prefixsum: sb_reduce -> NCCL all-gather -> seeded sb_scan, 3 passes",
+               "scan_then_carry": f"{world} contiguous shards; reduce: {red}; prefixsum: sb_scan -> NCCL all-gather -> sb_carry_add, 4 passes"}[B.strategy]
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "+".join(sorted({t for _, t, _ in legs})), "data": "synthetic (reference iota: in[i]=(T)i over the global index space, generated on device)",
             "config": {"workload": wl["name"], "elements_per_gpu": n, "elements_total": ntot, "legs": [leg_name(l) for l in legs],
                        "l2": "every leg streams >= 1 GiB, larger than the 126 MB L2; no flush needed",
-                       "parallelism": par, "scan_strategy": B.strategy, "strategy_note": B.strategy_note, "numa": B.numa},
+                       "parallelism": par, "scan_strategy": B.strategy, "reduce_exchange": ("fused" if (B.peer is not None and args.reduce_exchange == "fused" and world > 1) else ("nccl" if world > 1 else None)), "strategy_note": B.strategy_note, "numa": B.numa},
             "elements_per_s": round(len(legs) * ntot / (ms_per_step * 1e-3), 1),
             "frac_of_aggregate_measured_peak": round(value / (peak * world), 4),
             "verified": bool(ok), "verified_legs": main["verified"],
@@ -600,7 +604,7 @@ def run_e2e(B, legs, n):
             else:
                 d_in[t].copy_(h_in[t], non_blocking=True)  # H2D on the ctx stream (torch's current stream)
                 if op == "reduce":
-                    B.ops.reduce(d_in[t], d_red[t])
+                    B.ops.reduce(d_in[t], d_red[t], exchange=B.args.reduce_exchange)
                     h_red[t].copy_(d_red[t], non_blocking=True)
                 else:
                     B.ops.prefixsum(d_in[t], d_out[t], totals[t], carry[t], strategy=B.strategy)
@@ -765,6 +769,9 @@ def main():
     ap.add_argument("--no-config5", action="store_true")
     ap.add_argument("--no-replicas", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--reduce-exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1 reduction: all-reduce fused into the reduce kernel over NVLink peer memory (default; needs the peer group of "
+                         "--scan-strategy cyclic, else NCCL is used) or sb_reduce + NCCL all-reduce of one element")
     ap.add_argument("--scan-strategy", default="cyclic", choices=["cyclic", "reduce_then_scan", "scan_then_carry"],
                     help="N>1 prefix sum: block-cyclic 2-pass kernel with in-kernel NVLink exchange (default), 3-pass reduce -> all-gather -> seeded scan, "
                          "or the 4-pass scan -> all-gather -> carry-add")

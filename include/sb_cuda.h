@@ -303,6 +303,16 @@ int sb_scan_cyclic_i64(sb_ctx*, sb_peer* peer, const int64_t* in, int64_t* out, 
 int sb_scan_cyclic_f32(sb_ctx*, sb_peer* peer, const float* in, float* out, size_t n, int exclusive, const float* seed);
 int sb_scan_cyclic_f64(sb_ctx*, sb_peer* peer, const double* in, double* out, size_t n, int exclusive, const double* seed);
 int sb_scan_cyclic(sb_ctx*, sb_peer* peer, int dtype, const void* in, void* out, size_t n, int exclusive);
+/* Reduction with the all-reduce fused into the kernel: out[0] = sum over the inputs of ALL ranks of the peer group, on
+ * every rank.  The last block of sb_reduce's kernel stores this GPU's sum into every peer's mailbox over NVLink,
+ * waits for the other ranks' sums and adds them in rank order (identical floating-point result on every rank).
+ * Replaces sb_reduce + ncclAllReduce of one element (BASELINE.json north_star) by one launch per GPU.  A collective:
+ * every rank calls it, in the same order.  peer == NULL or a group of one: plain sb_reduce. */
+int sb_reduce_all_i32(sb_ctx*, sb_peer* peer, const int32_t* in, size_t n, int32_t* out);
+int sb_reduce_all_i64(sb_ctx*, sb_peer* peer, const int64_t* in, size_t n, int64_t* out);
+int sb_reduce_all_f32(sb_ctx*, sb_peer* peer, const float* in, size_t n, float* out);
+int sb_reduce_all_f64(sb_ctx*, sb_peer* peer, const double* in, size_t n, double* out);
+int sb_reduce_all(sb_ctx*, sb_peer* peer, int dtype, const void* in, size_t n, void* out);
 /* generate_input / verify() for that layout (n = elements of this rank, the same on every rank) */
 int sb_iota_cyclic_i32(sb_ctx*, int32_t* out, size_t n, size_t block, int world, int rank);
 int sb_iota_cyclic_i64(sb_ctx*, int64_t* out, size_t n, size_t block, int world, int rank);

@@ -17,6 +17,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -234,12 +236,16 @@ int sb_comm_join(sb_comm* c) {
 
 int sb_comm_reduce(sb_comm* c, int dtype, const void* const* in, const size_t* n, void* const* out) {
   if(!c || !in || !n || !out || dtype_size(dtype) == 0) return SB_ERR_BAD_ARG;
+  // default: the all-reduce is the tail of the reduce kernel itself (sb_reduce_all: peer-memory mailboxes over NVLink);
+  // SB_COMM_REDUCE=nccl, or a box without peer access, takes the literal recipe: sb_reduce + ncclAllReduce of one element
+  static const bool force_nccl = getenv("SB_COMM_REDUCE") && !strcmp(getenv("SB_COMM_REDUCE"), "nccl");
+  const bool fused = c->n > 1 && !force_nccl && ensure_peers(c) == SB_OK;
   if(int rc = comm_fork(c); rc != SB_OK) return rc;
   for(int r = 0; r < c->n; ++r) {
-    int rc = reduce_call(c->ctx[r], dtype, in[r], n[r], out[r]);
+    int rc = fused ? sb_reduce_all(c->ctx[r], c->peers[r], dtype, in[r], n[r], out[r]) : reduce_call(c->ctx[r], dtype, in[r], n[r], out[r]);
     if(rc != SB_OK) return comm_fail(c, rc);
   }
-  if(c->n > 1) {
+  if(c->n > 1 && !fused) {
     if(nccl().GroupStart() != ncclSuccess) return comm_fail(c, SB_ERR_NCCL);
     bool ok = true;
     for(int r = 0; r < c->n && ok; ++r)

@@ -21,11 +21,16 @@
 //    within the stated tolerance but not bit-reproducible run to run.  sb_ctx_set_deterministic(ctx, 1)
 //    selects the static chunk assignment instead: fixed summation order, bit-reproducible, ~3 % slower
 //    (i32 6.76 vs 6.97, f64 7.11 vs 7.25 TB/s).
+//  - sb_reduce_all_<T> (several GPUs): the last block does not stop at this GPU's sum.  It stores the sum into the
+//    mailbox of every peer (st.relaxed.sys over NVLink, sb_peer.cuh), waits for the other ranks' sums in its own
+//    mailbox and adds them in rank order: the all-reduce is the tail of the same kernel, no NCCL call, ~3 us
+//    instead of a separate collective launch.
 //  - the loads are `volatile` asm so that the batch is issued back to back; with plain asm nvcc sank
 //    part of the batch next to its first use for int32 and fp64 (5.85 / 5.6 TB/s).
 #include <cstdlib>
+#include <cstring>
 
-#include "sb_common.cuh"
+#include "sb_peer.cuh"
 
 namespace {
 
@@ -50,7 +55,7 @@ __device__ __forceinline__ A block_sum(A v, A* smem) {
 // tickets[0] = CTAs done, tickets[1] = next chunk
 template <typename A, int NT, int UNROLL, bool TICKETED>
 __global__ void __launch_bounds__(NT) reduce_kernel(const A* __restrict__ in, size_t n, A* __restrict__ partials,
-    unsigned int* __restrict__ tickets, A* __restrict__ out) {
+    unsigned int* __restrict__ tickets, A* __restrict__ out, const __grid_constant__ ReducePeers rp) {
   constexpr int VEC = 16 / sizeof(A);
   __shared__ A smem[NT / 32];
   __shared__ bool is_last;
@@ -137,6 +142,7 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const A* __restrict__ in, si
     for(unsigned int i = threadIdx.x; i < gridDim.x; i += NT) p += __ldcg(partials + i);
     __syncthreads();  // smem reuse
     A total = block_sum<A, NT>(p, smem);
+    if(rp.world > 1 && threadIdx.x < 32) total = mailbox_allreduce<A>(total, rp);  // warp 0 holds the block sum
     if(threadIdx.x == 0) {
       out[0] = total;
       tickets[0] = 0u;  // every CTA has drawn its last ticket and signed off: re-arm for the next launch
@@ -146,9 +152,10 @@ __global__ void __launch_bounds__(NT) reduce_kernel(const A* __restrict__ in, si
 }
 
 template <typename T>
-int reduce_impl(sb_ctx* ctx, const T* in, size_t n, T* out) {
+int reduce_impl(sb_ctx* ctx, sb_peer* peer, const T* in, size_t n, T* out) {
   using A = typename sb_arith<T>::type;
   if(!ctx || !out || (n && !in)) return SB_ERR_BAD_ARG;
+  if(peer && peer->ctx != ctx) return SB_ERR_BAD_ARG;
   if(!sb::aligned_to(in, sizeof(T)) || !sb::aligned_to(out, sizeof(T))) return SB_ERR_MISALIGNED;
   sb_device_guard guard(ctx->device);
   constexpr int VEC = 16 / sizeof(T);
@@ -165,10 +172,29 @@ int reduce_impl(sb_ctx* ctx, const T* in, size_t n, T* out) {
   const A* ain = reinterpret_cast<const A*>(in);
   A* apart = reinterpret_cast<A*>(ctx->partials);
   A* aout = reinterpret_cast<A*>(out);
+  ReducePeers rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.world = 1;
+  if(peer && peer->world > 1) {
+    for(int d = 0; d < peer->world; ++d)
+      if(!peer->connected[d]) return SB_ERR_PEER;
+    // two planes alternate: a rank can enter all-reduce k+2 only after every rank has written k+1, i.e. has finished
+    // (and read everything of) all-reduce k, the last user of the plane
+    const uint32_t tag = ++peer->red_seq;
+    const size_t plane = CY_REDUCE_OFFSET + (size_t)(tag & 1u) * CY_MAX_WORLD * 16;
+    for(int d = 0; d < peer->world; ++d)
+      rp.slot[d] = reinterpret_cast<unsigned long long*>(static_cast<char*>(peer->peer_base[d]) + plane) + 2 * peer->rank;
+    rp.mine = reinterpret_cast<const unsigned long long*>(static_cast<char*>(peer->base) + plane);
+    rp.world = peer->world;
+    rp.rank = peer->rank;
+    rp.tag = tag;
+    rp.timeout_ns = sb_peer_timeout_ns();
+    rp.err = ctx->err_dev;
+  }
   if(deterministic)
-    reduce_kernel<A, RED_NT, RED_UNROLL, false><<<(unsigned)blocks, RED_NT, 0, ctx->stream>>>(ain, n, apart, ctx->reduce_ticket, aout);
+    reduce_kernel<A, RED_NT, RED_UNROLL, false><<<(unsigned)blocks, RED_NT, 0, ctx->stream>>>(ain, n, apart, ctx->reduce_ticket, aout, rp);
   else
-    reduce_kernel<A, RED_NT, RED_UNROLL, true><<<(unsigned)blocks, RED_NT, 0, ctx->stream>>>(ain, n, apart, ctx->reduce_ticket, aout);
+    reduce_kernel<A, RED_NT, RED_UNROLL, true><<<(unsigned)blocks, RED_NT, 0, ctx->stream>>>(ain, n, apart, ctx->reduce_ticket, aout, rp);
   SB_CHECK_LAUNCH(ctx);
   return SB_OK;
 }
@@ -176,8 +202,22 @@ int reduce_impl(sb_ctx* ctx, const T* in, size_t n, T* out) {
 }  // namespace
 
 extern "C" {
-int sb_reduce_i32(sb_ctx* c, const int32_t* in, size_t n, int32_t* out) { return reduce_impl<int32_t>(c, in, n, out); }
-int sb_reduce_i64(sb_ctx* c, const int64_t* in, size_t n, int64_t* out) { return reduce_impl<int64_t>(c, in, n, out); }
-int sb_reduce_f32(sb_ctx* c, const float* in, size_t n, float* out) { return reduce_impl<float>(c, in, n, out); }
-int sb_reduce_f64(sb_ctx* c, const double* in, size_t n, double* out) { return reduce_impl<double>(c, in, n, out); }
+int sb_reduce_i32(sb_ctx* c, const int32_t* in, size_t n, int32_t* out) { return reduce_impl<int32_t>(c, nullptr, in, n, out); }
+int sb_reduce_i64(sb_ctx* c, const int64_t* in, size_t n, int64_t* out) { return reduce_impl<int64_t>(c, nullptr, in, n, out); }
+int sb_reduce_f32(sb_ctx* c, const float* in, size_t n, float* out) { return reduce_impl<float>(c, nullptr, in, n, out); }
+int sb_reduce_f64(sb_ctx* c, const double* in, size_t n, double* out) { return reduce_impl<double>(c, nullptr, in, n, out); }
+
+int sb_reduce_all_i32(sb_ctx* c, sb_peer* p, const int32_t* in, size_t n, int32_t* out) { return reduce_impl<int32_t>(c, p, in, n, out); }
+int sb_reduce_all_i64(sb_ctx* c, sb_peer* p, const int64_t* in, size_t n, int64_t* out) { return reduce_impl<int64_t>(c, p, in, n, out); }
+int sb_reduce_all_f32(sb_ctx* c, sb_peer* p, const float* in, size_t n, float* out) { return reduce_impl<float>(c, p, in, n, out); }
+int sb_reduce_all_f64(sb_ctx* c, sb_peer* p, const double* in, size_t n, double* out) { return reduce_impl<double>(c, p, in, n, out); }
+int sb_reduce_all(sb_ctx* c, sb_peer* p, int dtype, const void* in, size_t n, void* out) {
+  switch(dtype) {
+  case SB_I32: return sb_reduce_all_i32(c, p, (const int32_t*)in, n, (int32_t*)out);
+  case SB_I64: return sb_reduce_all_i64(c, p, (const int64_t*)in, n, (int64_t*)out);
+  case SB_F32: return sb_reduce_all_f32(c, p, (const float*)in, n, (float*)out);
+  case SB_F64: return sb_reduce_all_f64(c, p, (const double*)in, n, (double*)out);
+  default: return SB_ERR_BAD_ARG;
+  }
+}
 }

@@ -477,7 +477,7 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         bool open[K];
         A warp_agg;
         bool warp_has_head;
-        tile_pass1<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+        tile_pass1<A, MODE, K, MODE == MODE_FLAGS>(v, hf, carry_in, open, warp_agg, warp_has_head);
         // The tile lives in registers now (pass 1 consumed every ring read): hand the stage back BEFORE
         // waiting for the prefix, so that the producer can refill it during the look-back wait.  ncu showed
         // ~45 % of the warp samples in mbarrier wait loops with one 64 KB stage in flight per SM at most.
@@ -596,7 +596,7 @@ scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg
     bool open[K];
     A warp_agg;
     bool warp_has_head;
-    tile_pass1<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+    tile_pass1<A, MODE, K, (MODE == MODE_FLAGS || sizeof(A) == 8)>(v, hf, carry_in, open, warp_agg, warp_has_head);
     if(lane == 0) {
       mbar_arrive(smem_u32(&empty_bar[stage]));  // the tile lives in registers now
       s_wagg[slot][warp] = warp_agg;

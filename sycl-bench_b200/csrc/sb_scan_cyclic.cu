@@ -34,6 +34,7 @@
 #include <cstring>
 #include <new>
 
+#include "sb_peer.cuh"
 #include "sb_scan_tile.cuh"
 
 #ifndef SB_CY_NW
@@ -54,81 +55,16 @@
 #define SB_CY_BLOAD 0
 #endif
 
-constexpr int CY_MAX_WORLD = 16;
-constexpr int CY_MAX_ROUNDS = 16384;  // 16384 x 10.4 MB = 170 GB per GPU
-constexpr size_t CY_STARTED_BYTES = 256;
-
-struct sb_peer {
-  sb_ctx* ctx = nullptr;
-  int rank = 0, world = 1;
-  void* base = nullptr;  // own mailbox: started[world] | plane 0 | plane 1
-  size_t bytes = 0;
-  void* peer_base[CY_MAX_WORLD] = {};
-  bool ipc_opened[CY_MAX_WORLD] = {};
-  bool connected[CY_MAX_WORLD] = {};
-  uint32_t op_seq = 0;
-};
-
 namespace {
 using namespace sbscan;
 
 constexpr int CY_NW = SB_CY_NW, CY_K = SB_CY_K, CY_STAGES = SB_CY_STAGES;
 constexpr int CY_NSLOT = 8;      // ring of per-tile slots (warp sums, tile prefix); look-ahead D <= CY_NSLOT - 2
 constexpr int CY_MAX_DEPTH = CY_NSLOT - 2;
-constexpr int CY_TIMEOUT_MS = 8000;  // default; SB_CYCLIC_TIMEOUT_MS overrides (tests)
-
 struct PeerTable {
   unsigned long long* mbox[CY_MAX_WORLD];     // plane of the current operation in peer d's mailbox
   unsigned long long* started[CY_MAX_WORLD];  // started[world] array of peer d
 };
-
-size_t plane_bytes(int world) { return (size_t)CY_MAX_ROUNDS * world * 16; }
-size_t mailbox_bytes(int world) { return CY_STARTED_BYTES + 2 * plane_bytes(world); }
-
-// ---- polling with a deadline -------------------------------------------------------------------------------------
-struct Deadline {
-  unsigned spins = 0;
-  unsigned long long t0 = 0, limit_ns;
-  __device__ explicit Deadline(unsigned long long ns) : limit_ns(ns) {}
-  // true once the caller has been polling for longer than limit_ns in total (looked at every 256 passes)
-  __device__ __forceinline__ bool expired() {
-    if((++spins & 255u) != 0) return false;
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    if(t0 == 0) {
-      t0 = t;
-      return false;
-    }
-    return t - t0 > limit_ns;
-  }
-};
-
-__device__ __forceinline__ void mbox_load(const unsigned long long* p, unsigned long long& w0, unsigned long long& w1) {
-  asm volatile("ld.relaxed.sys.global.v2.u64 {%0,%1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
-}
-__device__ __forceinline__ void mbox_store(unsigned long long* p, unsigned long long w0, unsigned long long w1) {
-  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
-}
-template <typename A> __device__ __forceinline__ void mbox_pack(A v, uint32_t tag, unsigned long long& w0, unsigned long long& w1) {
-  const unsigned long long b = (unsigned long long)bits_of(v);  // 4-byte types: high half is zero
-  w0 = ((unsigned long long)tag << 32) | (b & 0xffffffffull);
-  w1 = ((unsigned long long)tag << 32) | (b >> 32);
-}
-template <typename A> __device__ __forceinline__ A mbox_unpack(unsigned long long w0, unsigned long long w1) {
-  if(sizeof(A) == 4) return from_bits32<A>((uint32_t)w0);
-  return from_bits64<A>((w0 & 0xffffffffull) | (w1 << 32));
-}
-template <> __device__ __forceinline__ uint32_t mbox_unpack<uint32_t>(unsigned long long w0, unsigned long long) { return (uint32_t)w0; }
-template <> __device__ __forceinline__ float mbox_unpack<float>(unsigned long long w0, unsigned long long) { return __uint_as_float((uint32_t)w0); }
-template <> __device__ __forceinline__ unsigned long long mbox_unpack<unsigned long long>(unsigned long long w0, unsigned long long w1) {
-  return (w0 & 0xffffffffull) | (w1 << 32);
-}
-template <> __device__ __forceinline__ double mbox_unpack<double>(unsigned long long w0, unsigned long long w1) {
-  return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-}
-__device__ __forceinline__ bool mbox_ready(unsigned long long w0, unsigned long long w1, uint32_t tag) {
-  return (uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag;
-}
 
 // Warp-collective: sum of the aggregates desc[0 .. count) of one round, in a fixed order (lane-strided partial sums,
 // then the xor tree), polling until every descriptor carries `epoch`.  All loads of a pass are issued back to back.
@@ -500,7 +436,7 @@ int scan_cyclic_impl(sb_ctx* ctx, sb_peer* peer, const T* in, T* out, size_t n, 
   for(int d = 0; d < peer->world; ++d) {
     char* b = static_cast<char*>(peer->peer_base[d]);
     pt.started[d] = reinterpret_cast<unsigned long long*>(b);
-    pt.mbox[d] = reinterpret_cast<unsigned long long*>(b + CY_STARTED_BYTES + (tag & 1u) * plane_bytes(peer->world));
+    pt.mbox[d] = reinterpret_cast<unsigned long long*>(b + CY_HEADER_BYTES + (tag & 1u) * plane_bytes(peer->world));
   }
   // look-ahead in rounds and L2 policies: defaults from the measurements in profiles/ (r02); the env knobs exist for tuning runs
   static const int env_depth = env_int("SB_CYCLIC_DEPTH", 0, 0, CY_MAX_DEPTH), env_hint = env_int("SB_CYCLIC_HINT", -1, -1, 1);
@@ -514,8 +450,7 @@ int scan_cyclic_impl(sb_ctx* ctx, sb_peer* peer, const T* in, T* out, size_t n, 
   int world = peer->world, rank = peer->rank;
   uint32_t tg = tag;
   unsigned* err = ctx->err_dev;
-  static const int env_timeout_ms = env_int("SB_CYCLIC_TIMEOUT_MS", CY_TIMEOUT_MS, 1, 600000);
-  unsigned long long timeout_ns = (unsigned long long)env_timeout_ms * 1000000ull;
+  unsigned long long timeout_ns = sb_peer_timeout_ns();
   void* args[] = {(void*)&ain, (void*)&aout, (void*)&n, (void*)&exclusive, (void*)&aseed, (void*)&desc, (void*)&epoch, (void*)&num_tiles, (void*)&g,
       (void*)&D, (void*)&hint, (void*)&pt, (void*)&world, (void*)&rank, (void*)&tg, (void*)&err, (void*)&timeout_ns};
   // cooperative launch: all CTAs co-resident (the look-back and leader warps wait for other CTAs of the grid)
@@ -534,6 +469,11 @@ size_t dtype_size(int dtype) {
 }
 
 }  // namespace
+
+unsigned long long sb_peer_timeout_ns() {
+  static const int ms = env_int("SB_CYCLIC_TIMEOUT_MS", CY_TIMEOUT_MS, 1, 600000);
+  return (unsigned long long)ms * 1000000ull;
+}
 
 void sb_ctx_release_self_peer(sb_ctx* ctx) {
   if(ctx->self_peer) {

@@ -285,7 +285,11 @@ __device__ __forceinline__ void tile_pass1_chained(const A (&v)[K][16 / sizeof(A
   warp_has_head = !warp_open;
 }
 
-template <typename A, int MODE, int K>
+// UNCHAINED: chunks that hold heads also take the K independent row scans below (ILP K instead of K dependent
+// shuffle chains) at the price of the per-row totals / head masks in registers.  Measured at 2^28
+// (profiles/r02_ops_v2*.jsonl): explicit flags +4..5 % (32-bit), 64-bit independent tiles +4.5..7 %, but the
+// implicit-head look-back kernel loses 6-13 % (96-register cap: spills), so the callers choose.
+template <typename A, int MODE, int K, bool UNCHAINED = false>
 __device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], A (&carry_in)[K], bool (&open)[K],
     A& warp_agg, bool& warp_has_head) {
   if(MODE != MODE_PLAIN) {
@@ -299,10 +303,10 @@ __device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], cons
       return;
     }
 #ifndef SB_SCAN_UNCHAINED
-    // (SB_SCAN_UNCHAINED: fall through to the K independent row scans below also when the chunk holds heads —
-    // ILP K instead of K dependent shuffle chains, at the price of the per-row totals / head masks in registers)
-    tile_pass1_chained<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
-    return;
+    if(!UNCHAINED) {
+      tile_pass1_chained<A, MODE, K>(v, hf, carry_in, open, warp_agg, warp_has_head);
+      return;
+    }
 #endif
   }
   constexpr int VEC = 16 / sizeof(A);

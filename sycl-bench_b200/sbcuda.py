@@ -100,6 +100,9 @@ def lib() -> C.CDLL:
         getattr(L, f"sb_check_iota_cyclic_{t}").argtypes = [vp, vp, sz, sz, i, i, i, C.c_double, vp]
         getattr(L, f"sb_scan_cyclic_{t}").argtypes = [vp, vp, vp, vp, sz, i, vp]
     L.sb_scan_cyclic.argtypes = [vp, vp, i, vp, vp, sz, i]
+    for t in DTYPES[1:]:
+        getattr(L, f"sb_reduce_all_{t}").argtypes = [vp, vp, vp, sz, vp]
+    L.sb_reduce_all.argtypes = [vp, vp, i, vp, sz, vp]
     L.sb_cyclic_block_elems.argtypes = [vp, i]
     L.sb_cyclic_block_elems.restype = sz
     L.sb_peer_create.argtypes = [vp, i, i, C.POINTER(vp)]
@@ -236,6 +239,13 @@ class Context:
         t = dtype or dtype_of(x)
         n = x.numel() if n is None else n
         _check(getattr(lib(), f"sb_reduce_{t}")(self._h, _ptr(x), n, _ptr(out)))
+        return out
+
+    def reduce_all(self, x, out, peer: "Optional[Peer]" = None, n: Optional[int] = None, dtype: Optional[str] = None):
+        """out[0] = sum over the inputs of ALL ranks of the peer group (all-reduce fused into the reduce kernel)."""
+        t = dtype or dtype_of(x)
+        n = x.numel() if n is None else n
+        _check(getattr(lib(), f"sb_reduce_all_{t}")(self._h, peer._h if peer is not None else None, _ptr(x), n, _ptr(out)))
         return out
 
     def copy(self, dst, src, nbytes: Optional[int] = None):

@@ -1,6 +1,8 @@
 """Multi-GPU data path: one process per GPU, contiguous shards, ONE tiny exchange per operation.
 
-    reduction : local sb_reduce  -> all-reduce(sum) of one element per rank            (traffic N*s/P per GPU)
+    reduction : "fused": sb_reduce_all — the last block of the reduce kernel exchanges the per-GPU sums through the
+                         peer-memory mailboxes (NVLink) and adds them in rank order: one launch, no collective call
+                "nccl" : local sb_reduce -> all-reduce(sum) of one element per rank     (traffic N*s/P per GPU)
     prefix sum: "reduce_then_scan": local sb_reduce -> all-gather of the P shard totals
                                     -> sb_exclusive_carry -> sb_scan seeded with the carry  (3*N*s/P per GPU)
                 "scan_then_carry" : local sb_scan -> all-gather of the shard totals
@@ -56,10 +58,11 @@ def cyclic_global_indices(n: int, block: int, world: int, rank: int):
 
 class ShardedOps:
     def __init__(self, dist, rank: int, world: int, reduce: Callable, scan: Callable, carry_add: Callable, exclusive_carry: Callable,
-                 scan_cyclic: Callable | None = None, segreduce: Callable | None = None, segscan: Callable | None = None):
+                 scan_cyclic: Callable | None = None, segreduce: Callable | None = None, segscan: Callable | None = None,
+                 reduce_all: Callable | None = None):
         self.dist, self.rank, self.world = dist, rank, world
         self._reduce, self._scan, self._carry_add, self._exclusive_carry = reduce, scan, carry_add, exclusive_carry
-        self._scan_cyclic, self._segreduce, self._segscan = scan_cyclic, segreduce, segscan
+        self._scan_cyclic, self._segreduce, self._segscan, self._reduce_all = scan_cyclic, segreduce, segscan, reduce_all
 
     # -- replicas: shards cut on segment boundaries need nothing from each other
     def foreach_segreduce(self, x, seg_len: int):
@@ -86,8 +89,12 @@ class ShardedOps:
         if seg_len <= 0 or n % seg_len != 0:
             raise ValueError(f"shard of {n} elements is not cut on segment boundaries (segment length {seg_len})")
 
-    def reduce(self, x, out):
-        """out[0] = sum over ALL shards (every rank gets it)."""
+    def reduce(self, x, out, exchange: str = "fused"):
+        """out[0] = sum over ALL shards (every rank gets it).  exchange: "fused" (in-kernel, needs a peer group;
+        falls back to "nccl" without one) or "nccl" (torch.distributed all-reduce of one element)."""
+        if exchange == "fused" and self._reduce_all is not None and self.world > 1:
+            self._reduce_all(x, out)
+            return out
         self._reduce(x, out)
         if self.world > 1:
             self.dist.all_reduce(out)
@@ -151,6 +158,7 @@ def for_context(ctx, dist, rank: int, world: int, peer=None) -> ShardedOps:
         carry_add=lambda y, c: ctx.carry_add(y, c),
         exclusive_carry=lambda t, r, c: ctx.exclusive_carry(t, r, c),
         scan_cyclic=scan_cyclic,
+        reduce_all=(lambda x, out: ctx.reduce_all(x, out, peer=peer)) if peer is not None else None,
         segreduce=lambda x, L: ctx.segreduce(x, L),
         segscan=lambda x, y, L, exclusive: ctx.segscan(x, y, seg_len=L, exclusive=exclusive),
     )

@@ -196,6 +196,43 @@ print("AFTER", int(y[-1].item()) == n)
     assert "AFTER True" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("t", ALL4)
+def test_reduce_all_two_ranks_on_one_gpu(pkg, O, t):
+    """sb_reduce_all: the all-reduce is the tail of the reduce kernel (peer mailboxes).  Two ranks as two contexts /
+    streams on ONE device: the last block of one kernel waits for the other kernel's sum.  Integers exact; floating
+    point identical on both ranks (the sums are added in rank order) and within tolerance; several calls in a row use
+    both mailbox planes."""
+    torch.cuda.set_device(0)
+    c0, c1 = pkg.Context(0, pkg.Context.OWNED_STREAM), pkg.Context(0, pkg.Context.OWNED_STREAM)
+    p0, p1 = pkg.Peer(c0, 0, 2), pkg.Peer(c1, 1, 2)
+    p0.connect_local(p1)
+    p1.connect_local(p0)
+    try:
+        for n in (1000, (1 << 22) + 77):
+            h0, h1 = O.iota(t, n, 5), O.iota(t, n, 5 + n)
+            x0, x1 = torch.from_numpy(h0).cuda(), torch.from_numpy(h1).cuda()
+            o0, o1 = torch.zeros(1, dtype=TORCH[t], device="cuda"), torch.zeros(1, dtype=TORCH[t], device="cuda")
+            torch.cuda.synchronize()
+            for _ in range(3):
+                c0.reduce_all(x0, o0, peer=p0)
+                c1.reduce_all(x1, o1, peer=p1)
+                c0.sync()
+                c1.sync()
+                g0, g1 = o0.cpu().numpy()[0], o1.cpu().numpy()[0]
+                assert g0 == g1
+                if t[0] == "i":
+                    lo, hi = 5, 5 + 2 * n
+                    assert int(g0) == O.wrap(hi * (hi - 1) // 2 - lo * (lo - 1) // 2, t)
+                else:
+                    want = float(np.sum(h0.astype(np.float64)) + np.sum(h1.astype(np.float64)))
+                    assert abs(float(g0) - want) <= tol(t, 2 * n) * abs(want)
+    finally:
+        p0.close()
+        p1.close()
+        c0.close()
+        c1.close()
+
+
 # ---------------------------------------------------------------------------------------- >= 2 GPUs
 def _ngpus():
     return torch.cuda.device_count()
