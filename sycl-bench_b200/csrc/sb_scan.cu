@@ -291,6 +291,7 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
   __shared__ A s_wagg[WS_NSLOT][NW];
   __shared__ int s_wflag[WS_NSLOT][NW];
   __shared__ A s_tprefix[WS_NSLOT];
+  __shared__ A s_wprefix[WS_NSLOT][NW];  // plain scans: per-warp prefixes written by the look-back warp (tile prefix included)
   __shared__ __align__(8) unsigned long long xchg_bar;  // workers' barrier of "lazy" tiles (below)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -363,7 +364,9 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
       mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(i / WS_NSLOT) & 1u);
       A tile_agg = A(0);
       bool tile_has_head = false;
-      if(!lazy) {
+      if(MODE == MODE_PLAIN) {
+        tile_agg = warp_prefixes<A, NW>(s_wagg[slot], nullptr, A(0), false);
+      } else if(!lazy) {
         A my_prefix;
         bool my_open;
         combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], -1, my_prefix, my_open, tile_agg, tile_has_head);
@@ -372,6 +375,11 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
       if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | (tile_has_head ? ST_INCL : ST_AGG), tile_agg);
       A p = A(0);
       if(!on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed);
+      if(MODE == MODE_PLAIN) {
+        (void)warp_prefixes<A, NW>(s_wagg[slot], s_wprefix[slot], p, true);
+        __threadfence_block();  // every writing lane orders its s_wprefix store before the warp barrier; lane 0 then releases
+        __syncwarp();
+      }
       if(lane == 0) {
         if((tile + 1) % G == 0)
           Desc<A>::store(const_cast<typename Desc<A>::word*>(rdesc) + tile / G, (epoch << 2) | ST_INCL, tile_has_head ? tile_agg : p + tile_agg);
@@ -502,11 +510,17 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         } else {
           mbar_wait(smem_u32(&agg_bar[slot]), par);
         }
-        A my_prefix, tile_agg;
-        bool my_open, tile_has_head;
-        combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], warp, my_prefix, my_open, tile_agg, tile_has_head);
-        const A warp_prefix = my_prefix + (my_open ? tile_prefix : A(0));
-        tile_pass2_store<A, MODE, true, K>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, exclusive);
+        if(MODE == MODE_PLAIN && use_lookback) {
+          const A warp_prefix = s_wprefix[slot][warp];
+          if(exclusive) tile_pass2_store<A, MODE, true, K, false, 1>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, 1);
+          else tile_pass2_store<A, MODE, true, K, false, 0>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, 0);
+        } else {
+          A my_prefix, tile_agg;
+          bool my_open, tile_has_head;
+          combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], warp, my_prefix, my_open, tile_agg, tile_has_head);
+          const A warp_prefix = my_prefix + (my_open ? tile_prefix : A(0));
+          tile_pass2_store<A, MODE, true, K>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, exclusive);
+        }
       }
     }
   }

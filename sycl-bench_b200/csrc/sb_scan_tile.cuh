@@ -367,7 +367,9 @@ __device__ __forceinline__ void tile_pass1(const A (&v)[K][16 / sizeof(A)], cons
 
 // pass 2: rescan with the known carry, 128-bit coalesced stores from registers
 // (HINT: the 128-bit stores carry an L2 cache policy, see sb_scan_cyclic.cu)
-template <typename A, int MODE, bool ALIGNED, int K, bool HINT = false>
+// (EXCL: -1 = the run-time `exclusive` flag decides per element — a 64-bit select costs two SEL per element, 16 % of the
+// instructions of the 64-bit global scans in ncu —, 0 / 1 = decided at compile time by the caller's branch)
+template <typename A, int MODE, bool ALIGNED, int K, bool HINT = false, int EXCL = -1>
 __device__ __forceinline__ void tile_pass2_store(const A (&v)[K][16 / sizeof(A)], const unsigned (&hf)[K], const A (&carry_in)[K],
     const bool (&open)[K], A warp_prefix, size_t wbase, bool full_tile, size_t n, A* out, int exclusive, unsigned long long policy = 0) {
   constexpr int VEC = 16 / sizeof(A);
@@ -381,7 +383,7 @@ __device__ __forceinline__ void tile_pass2_store(const A (&v)[K][16 / sizeof(A)]
       if(MODE != MODE_PLAIN && ((hf[j] >> c) & 1u)) r = A(0);
       const A e = r;
       r += v[j][c];
-      o.v[c] = exclusive ? e : r;
+      o.v[c] = (EXCL < 0 ? exclusive != 0 : EXCL != 0) ? e : r;
     }
     if(ALIGNED && (full_tile || idx + VEC <= n)) {
       if(HINT) {
@@ -396,6 +398,26 @@ __device__ __forceinline__ void tile_pass2_store(const A (&v)[K][16 / sizeof(A)]
         if(idx + c < n) out[idx + c] = o.v[c];
     }
   }
+}
+
+// Plain scans: one warp turns the NW per-warp sums of a tile into per-warp PREFIXES (tile prefix included), so that a
+// worker reads one value instead of walking all NW sums with selects (combine_warps below: 18 x (LDS, add, 2-4 SEL)
+// per lane and tile).  Returns the tile aggregate.  wprefix[w] = tile_prefix + sum of wagg[0..w).
+template <typename A, int NW>
+__device__ __forceinline__ A warp_prefixes(const A* wagg, A* wprefix, A tile_prefix, bool write) {
+  static_assert(NW <= 32, "one lane per worker warp");
+  const int lane = threadIdx.x & 31;
+  const A mine = lane < NW ? wagg[lane] : A(0);
+  A incl = mine;
+#pragma unroll
+  for(int d = 1; d < 32; d <<= 1) {
+    const A up = sb::shfl_up(incl, d);
+    if(lane >= d) incl += up;
+  }
+  A excl = sb::shfl_up(incl, 1);
+  if(lane == 0) excl = A(0);
+  if(write && lane < NW) wprefix[lane] = tile_prefix + excl;
+  return sb::shfl_idx(incl, 31);
 }
 
 // prefix of the warps in front of `warp` inside a tile and the tile's own (aggregate, has-head)

@@ -75,17 +75,20 @@ def test_gpu_copy_rejects_partial_overlap(ctx, pkg):
 
 @pytest.mark.gpu
 def test_dram_element_count_follows_upstream_per_dims(tmp_path):
-    """--size=10: upstream's getBufferSize divides by sizeof(T) at a different place per dimensionality
-    (/root/reference/micro/DRAM.cpp:11-22): 250 / 250 / 200 fp32 elements, 125 / 120 / 100 fp64 elements."""
+    """--size=1001: upstream's getBufferSize divides by sizeof(T) at a different place per dimensionality
+    (/root/reference/micro/DRAM.cpp:11-22), so the three rows of a type copy different element counts.  The CSV prints
+    the throughput metric (2 x buffer GiB) with six decimals, enough to tell the counts apart at this size."""
     from oracle import oracle as O
 
-    out = tmp_path / "dram10.csv"
-    r = subprocess.run([os.path.join(BIN, "DRAM"), "--size=10", "--num-runs=1", f"--output={out}"], capture_output=True, text=True, timeout=600)
+    out = tmp_path / "dram1001.csv"
+    r = subprocess.run([os.path.join(BIN, "DRAM"), "--size=1001", "--num-runs=1", f"--output={out}"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     rows = O.parse_csv(str(out))
-    want = {"fp32": (250, 250, 200), "fp64": (125, 120, 100)}
+    p = 1001
     for t, size in (("fp32", 4), ("fp64", 8)):
+        want = (p * p * p // size, (p * p // size) * p, (p // size) * p * p)
+        assert len(set(want)) == 3
         for d in (1, 2, 3):
             row = rows[f"MicroBench_DRAM_{t}_{d}"]
             assert row["Verification"] == "PASS"
-            assert abs(float(row["throughput-metric"]) - 2 * want[t][d - 1] * size / 2**30) < 1e-12
+            assert abs(float(row["throughput-metric"]) - 2 * want[d - 1] * size / 2**30) < 6e-7, (t, d, row["throughput-metric"])
