@@ -90,6 +90,19 @@ constexpr int WS_NW_NARROW = SB_WS_NW_NARROW;
 #define SB_WS_NW_FLAGS SB_WS_NW  // worker warps of the explicit-flag instantiation
 #endif
 constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
+// A/B switches of two instruction-count optimisations of the plain look-back scan, measured at 2^28
+// (profiles/r02_ops_v6_wprefix_ab.jsonl):
+//   SB_EXCL_T  exclusive flag resolved at compile time in pass 2 (no 64-bit select per element): +1..2 %, ON.
+//   SB_WPREFIX per-warp prefixes computed once by the look-back warp instead of every worker lane walking the NW warp
+//              sums: 15 % fewer worker instructions for 64-bit types, but the two extra warp scans sit on the inter-CTA
+//              hand-over (aggregate -> descriptor, prefix -> workers) and the kernel LOSES 10-17 % (i32 6.30 -> 5.17,
+//              i64 6.18 -> 5.56 TB/s).  OFF: the chain, not the issue slots, bounds this kernel.
+#ifndef SB_WPREFIX
+#define SB_WPREFIX 0
+#endif
+#ifndef SB_EXCL_T
+#define SB_EXCL_T 1
+#endif
 #ifndef SB_WS_NW_LB64
 #define SB_WS_NW_LB64 14  // 64-bit types, segmented modes with look-back: 14 + 2 = 16 warps -> 128 registers per thread
 #endif
@@ -364,7 +377,7 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
       mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(i / WS_NSLOT) & 1u);
       A tile_agg = A(0);
       bool tile_has_head = false;
-      if(MODE == MODE_PLAIN) {
+      if(MODE == MODE_PLAIN && SB_WPREFIX) {
         tile_agg = warp_prefixes<A, NW>(s_wagg[slot], nullptr, A(0), false);
       } else if(!lazy) {
         A my_prefix;
@@ -375,7 +388,7 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
       if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | (tile_has_head ? ST_INCL : ST_AGG), tile_agg);
       A p = A(0);
       if(!on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed);
-      if(MODE == MODE_PLAIN) {
+      if(MODE == MODE_PLAIN && SB_WPREFIX) {
         (void)warp_prefixes<A, NW>(s_wagg[slot], s_wprefix[slot], p, true);
         __threadfence_block();  // every writing lane orders its s_wprefix store before the warp barrier; lane 0 then releases
         __syncwarp();
@@ -510,9 +523,18 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         } else {
           mbar_wait(smem_u32(&agg_bar[slot]), par);
         }
-        if(MODE == MODE_PLAIN && use_lookback) {
-          const A warp_prefix = s_wprefix[slot][warp];
-          if(exclusive) tile_pass2_store<A, MODE, true, K, false, 1>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, 1);
+        if(MODE == MODE_PLAIN && use_lookback && (SB_WPREFIX || SB_EXCL_T)) {
+          A warp_prefix;
+          if(SB_WPREFIX) {
+            warp_prefix = s_wprefix[slot][warp];
+          } else {
+            A my_prefix, tile_agg;
+            bool my_open, tile_has_head;
+            combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], warp, my_prefix, my_open, tile_agg, tile_has_head);
+            warp_prefix = my_prefix + tile_prefix;
+          }
+          if(!SB_EXCL_T) tile_pass2_store<A, MODE, true, K>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, exclusive);
+          else if(exclusive) tile_pass2_store<A, MODE, true, K, false, 1>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, 1);
           else tile_pass2_store<A, MODE, true, K, false, 0>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, 0);
         } else {
           A my_prefix, tile_agg;

@@ -165,8 +165,8 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
   constexpr int STAGE_BYTES = C::TILE_BYTES;
   extern __shared__ __align__(128) unsigned char ring[];  // CY_STAGES x STAGE_BYTES
   __shared__ __align__(8) unsigned long long full_bar[CY_STAGES], empty_bar[CY_STAGES], agg_bar[CY_NSLOT], prefix_bar[CY_NSLOT];
-  __shared__ A s_wagg[CY_NSLOT][NW];     // phase A: per-warp sums of a tile
-  __shared__ A s_wprefix[CY_NSLOT][NW];  // look-back warp: per-warp prefixes, tile prefix included
+  __shared__ A s_wagg[CY_NSLOT][NW];  // phase A: per-warp sums of a tile
+  __shared__ A s_tprefix[CY_NSLOT];   // look-back warp: prefix of the tile
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long pos = blockIdx.x;
@@ -244,7 +244,9 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
       const int slot = (int)(i % CY_NSLOT);
       const long long tile = pos + i * G;
       mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(i / CY_NSLOT) & 1u);
-      const A tile_agg = warp_prefixes<A, NW>(s_wagg[slot], nullptr, A(0), false);
+      A my_prefix, tile_agg;
+      bool my_open, tile_has_head;
+      combine_warps<A, MODE_PLAIN, NW>(s_wagg[slot], nullptr, -1, my_prefix, my_open, tile_agg, tile_has_head);
       if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | ST_AGG, tile_agg);
       if(leader) {
         // round total -> every rank's mailbox.  This comes BEFORE the leader's own look-back: the total depends on
@@ -284,10 +286,10 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
       }
       E += sb::warp_sum<A>(want_prev ? mbox_unpack<A>(p0, p1) : A(0));
       const A lower = sb::warp_sum<A>(want_cur ? mbox_unpack<A>(c0, c1) : A(0));
-      (void)warp_prefixes<A, NW>(s_wagg[slot], s_wprefix[slot], (E + lower) + local, true);
-      __threadfence_block();  // every writing lane orders its s_wprefix store before the warp barrier; lane 0 then releases
-      __syncwarp();
-      if(lane == 0) mbar_arrive(smem_u32(&prefix_bar[slot]));
+      if(lane == 0) {
+        s_tprefix[slot] = (E + lower) + local;
+        mbar_arrive(smem_u32(&prefix_bar[slot]));
+      }
     }
   } else {
     // ===== workers: per iteration phase A of tile `it` (from the ring), then phase B of tile it-D =====
@@ -348,7 +350,13 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
           if(lane == 0) mbar_arrive(smem_u32(&empty_bar[(int)((q - 1) % CY_STAGES)]));  // the tile lives in registers now
         }
         mbar_wait(smem_u32(&prefix_bar[slot]), (uint32_t)(b / CY_NSLOT) & 1u);
-        const A warp_prefix = s_wprefix[slot][warp];
+        // (the per-warp prefixes are NOT precomputed by the look-back warp: that was measured 10-17 % slower on the
+        // look-back kernel, sb_scan.cu SB_WPREFIX — the hand-over is the critical path, not the workers' issue slots)
+        const A tile_prefix = s_tprefix[slot];
+        A my_prefix, tile_agg;
+        bool my_open, tile_has_head;
+        combine_warps<A, MODE_PLAIN, NW>(s_wagg[slot], nullptr, warp, my_prefix, my_open, tile_agg, tile_has_head);
+        const A warp_prefix = my_prefix + tile_prefix;
         if(hint) {
           if(exclusive) tile_pass2_store<A, MODE_PLAIN, true, K, true, 1>(v, hf, carry_in, open, warp_prefix, bw, bfull, n, out, 1, stream);
           else tile_pass2_store<A, MODE_PLAIN, true, K, true, 0>(v, hf, carry_in, open, warp_prefix, bw, bfull, n, out, 0, stream);
