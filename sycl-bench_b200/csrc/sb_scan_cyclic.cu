@@ -240,28 +240,46 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
     }
     A E = A(0);
     if(seed) E = *seed;
+    // Publishing runs AHEAD of looking back.  The aggregate of round pa (and, in the leader, the round total T[pa]) goes
+    // out as soon as phase A of that round is complete — up to D rounds ahead of the look-back, also from inside the
+    // look-back's polling loop.  If a warp published round i+1 only after its look-back of round i, every total would wait
+    // for the lower ranks' totals of the round before: a chain across the ranks (rank g's T[i] after rank 0's T[i-g], rank
+    // 0's after rank P-1's T[i-2]) whose latency grows with P — the 64-bit leg went 0.84 / 0.88 / 0.93 ms at 2 / 4 / 8
+    // GPUs with the sequential loop (profiles/r02_scale_n*.json).
+    long long pa = 0, cur = 0;
+    auto publish = [&](long long must) {  // blocks until round `must` is out (-1: only what is ready)
+      while(pa < my_tiles) {
+        const int ls = (int)(pa % CY_NSLOT);
+        const uint32_t lp = (uint32_t)(pa / CY_NSLOT) & 1u;
+        if(pa <= must) {
+          mbar_wait(smem_u32(&agg_bar[ls]), lp);
+        } else {
+          if(pa > cur + D) break;  // phase A is at most D rounds ahead of the tile this warp owes a prefix for
+          if(!__all_sync(SB_FULL_MASK, mbar_test(smem_u32(&agg_bar[ls]), lp))) break;
+        }
+        A my_prefix, tile_agg;
+        bool my_open, tile_has_head;
+        combine_warps<A, MODE_PLAIN, NW>(s_wagg[ls], nullptr, -1, my_prefix, my_open, tile_agg, tile_has_head);
+        if(lane == 0) Desc<A>::store(desc + pos + pa * G, (epoch << 2) | ST_AGG, tile_agg);
+        if(leader) {
+          // round total -> every rank's mailbox; depends on nothing but this GPU's phase A
+          __syncwarp();
+          const long long left = num_tiles - pa * G;
+          const int count = (int)(left < G ? left : G);
+          const A total = sum_round_aggregates<A>(desc + pa * G, count, epoch, dl, err);
+          if(lane < world) {
+            unsigned long long w0, w1;
+            mbox_pack<A>(total, tag, w0, w1);
+            mbox_store(peers.mbox[lane] + (pa * world + rank) * 2, w0, w1);
+          }
+        }
+        ++pa;
+      }
+    };
     for(long long i = 0; i < my_tiles; ++i) {  // i is the round index of this CTA's i-th tile
       const int slot = (int)(i % CY_NSLOT);
-      const long long tile = pos + i * G;
-      mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(i / CY_NSLOT) & 1u);
-      A my_prefix, tile_agg;
-      bool my_open, tile_has_head;
-      combine_warps<A, MODE_PLAIN, NW>(s_wagg[slot], nullptr, -1, my_prefix, my_open, tile_agg, tile_has_head);
-      if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | ST_AGG, tile_agg);
-      if(leader) {
-        // round total -> every rank's mailbox.  This comes BEFORE the leader's own look-back: the total depends on
-        // nothing but this GPU's phase A, whereas the look-back waits for the lower ranks' totals of the same round
-        // (publishing afterwards would chain the ranks: P-1 NVLink latencies per round).
-        __syncwarp();
-        const long long left = num_tiles - i * G;
-        const int count = (int)(left < G ? left : G);
-        const A total = sum_round_aggregates<A>(desc + i * G, count, epoch, dl, err);
-        if(lane < world) {
-          unsigned long long w0, w1;
-          mbox_pack<A>(total, tag, w0, w1);
-          mbox_store(peers.mbox[lane] + (i * world + rank) * 2, w0, w1);
-        }
-      }
+      cur = i;
+      publish(i);
       // mailbox: lane l reads T[i-1][l] (all ranks, to advance E) and, if l < rank, T[i][l]
       unsigned long long p0 = 0, p1 = 0, c0 = 0, c1 = 0;
       const bool want_prev = i > 0 && lane < world, want_cur = lane < rank;
@@ -279,6 +297,7 @@ scan_cyclic_kernel(const A* in, A* out, size_t n, int exclusive, const A* __rest
           mbox_load(mine + (i * world + lane) * 2, c0, c1);
         }
         if(!__any_sync(SB_FULL_MASK, missing)) break;
+        publish(-1);  // do not sit on finished aggregates while waiting for other ranks
         if(__any_sync(SB_FULL_MASK, dl.expired())) {
           if(lane == 0) *err = 1u;
           break;
@@ -447,7 +466,7 @@ int scan_cyclic_impl(sb_ctx* ctx, sb_peer* peer, const T* in, T* out, size_t n, 
   }
   // look-ahead in rounds and L2 policies: defaults from the measurements in profiles/ (r02); the env knobs exist for tuning runs
   static const int env_depth = env_int("SB_CYCLIC_DEPTH", 0, 0, CY_MAX_DEPTH), env_hint = env_int("SB_CYCLIC_HINT", -1, -1, 1);
-  int D = env_depth > 0 ? env_depth : (peer->world > 1 ? 3 : 2);  // rounds of 10.4 MB: L2 keeps ~3 of them (profiles/r02_cyclic_variants.txt)
+  int D = env_depth > 0 ? env_depth : 2;  // rounds of 10.4 MB: L2 keeps ~3 of them (profiles/r02_cyclic_variants.txt); 8 GPUs: D=1/2/3 -> 7.00/7.00/6.87x on config 5
   int hint = env_hint >= 0 ? env_hint : 1;
   size_t grid = (size_t)G < tiles ? (size_t)G : tiles;
   const A* ain = reinterpret_cast<const A*>(in);
