@@ -21,8 +21,8 @@ except Exception as e:
 PY
 }
 for N in 1 2 4 8; do run $N n$N --no-cpu-baseline; done
-run 8 n8_rts --scan-strategy reduce_then_scan --no-e2e --no-replicas --no-cpu-baseline
 if [ -z "$QUICK" ]; then
+  run 8 n8_rts --scan-strategy reduce_then_scan --no-e2e --no-replicas --no-cpu-baseline
   timeout 900 python -m pytest tests/test_cyclic_gpu.py tests/test_comm_gpu.py -x -q -m gpu -k "comm_scan_cyclic or foreach or binaries" > $O/r02_scale_pytest.txt 2>&1
   tail -3 $O/r02_scale_pytest.txt
 fi
