@@ -441,7 +441,7 @@ def run_ours(args):
     dom_bytes = algorithmic_bytes(dom[0], dom[1], n, dom[2])
     achieved = dom_bytes / (leg_ms[dom_key] * 1e-3) / 1e9
     kernels = {
-        "single": "scan_ws_kernel<%s, plain> (sb_scan_%s: persistent warp-specialised TMA ring, round look-back)",
+        "single": "scan_ws_kernel<%s, plain> (sb_scan_%s: persistent warp-specialised TMA ring, round look-back over independent round totals)",
         "cyclic": "scan_cyclic_kernel<%s> (sb_scan_cyclic_%s: two-phase persistent TMA-ring kernel, tile re-read from L2, round totals exchanged over NVLink peer memory)",
         "reduce_then_scan": "reduce_kernel<%s> + NCCL all-gather + seeded scan_ws_kernel (sb_reduce_%s -> sb_scan)",
         "scan_then_carry": "scan_ws_kernel<%s> + NCCL all-gather + carry_add_kernel (sb_scan_%s -> sb_carry_add)",

@@ -100,6 +100,10 @@ constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
 #ifndef SB_WPREFIX
 #define SB_WPREFIX 0
 #endif
+//   SB_WS_TOTALS  plain look-back scans: independent round totals + publish-ahead instead of the chained round prefix
+#ifndef SB_WS_TOTALS
+#define SB_WS_TOTALS 1
+#endif
 #ifndef SB_EXCL_T
 #define SB_EXCL_T 1
 #endif
@@ -113,8 +117,10 @@ using namespace sbscan;
 
 // classic decoupled look-back by one full warp: sum the aggregates of the predecessors down to the
 // first tile whose inclusive prefix is known (ticketed kernel)
+// (every polling loop carries a deadline: a CTA that waits for a descriptor that never comes raises the ctx error flag and
+// carries on with what it has — sb_ctx_sync reports SB_ERR_TIMEOUT — instead of hanging the device)
 template <typename A>
-__device__ __forceinline__ A lookback(const typename Desc<A>::word* desc, long long tile, uint32_t epoch) {
+__device__ __forceinline__ A lookback(const typename Desc<A>::word* desc, long long tile, uint32_t epoch, Deadline& dl, unsigned* err) {
   const int lane = sb::lane_id();
   A prefix = A(0);
   long long pred = tile - 1 - lane;
@@ -129,8 +135,14 @@ __device__ __forceinline__ A lookback(const typename Desc<A>::word* desc, long l
     }
 #pragma unroll
     for(int w = 0; w < SCAN_WINDOW; ++w) {
-      if(pred - 32 * w >= 0) {
-        while((st[w] >> 2) != epoch) Desc<A>::load(desc + (pred - 32 * w), st[w], val[w]);
+      for(;;) {
+        const bool missing = pred - 32 * w >= 0 && (st[w] >> 2) != epoch;
+        if(missing) Desc<A>::load(desc + (pred - 32 * w), st[w], val[w]);
+        if(!__any_sync(SB_FULL_MASK, missing && (st[w] >> 2) != epoch)) break;
+        if(__any_sync(SB_FULL_MASK, dl.expired())) {
+          if(lane == 0) *err = 1u;
+          return prefix;
+        }
       }
       const unsigned incl = __ballot_sync(SB_FULL_MASK, (st[w] & 3u) == ST_INCL);
       if(incl) {
@@ -147,7 +159,7 @@ __device__ __forceinline__ A lookback(const typename Desc<A>::word* desc, long l
 // round look-back (persistent kernel), see the header comment
 template <typename A, int MODE>
 __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, const typename Desc<A>::word* rdesc, long long tile,
-    long long G, uint32_t epoch, const A* __restrict__ seed) {
+    long long G, uint32_t epoch, const A* __restrict__ seed, Deadline& dl, unsigned* err) {
   constexpr int U = SCAN_WINDOW;
   const int lane = sb::lane_id();
   const long long r = tile / G;
@@ -189,6 +201,10 @@ __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, 
       }
       if(lane == 0 && r > 0 && (rst >> 2) != epoch) Desc<A>::load(rdesc + (r - 1), rst, rval);  // keep the round prefix polling too
       if(!__any_sync(SB_FULL_MASK, missing)) break;
+      if(__any_sync(SB_FULL_MASK, dl.expired())) {
+        if(lane == 0) *err = 1u;
+        break;
+      }
     }
 #pragma unroll
     for(int u = 0; u < U; ++u) {
@@ -207,8 +223,14 @@ __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, 
   }
   A total = sb::warp_sum<A>(lane_sum);
   if(!head_found) {
-    if(lane == 0 && r > 0) {
-      while((rst >> 2) != epoch) Desc<A>::load(rdesc + (r - 1), rst, rval);
+    for(;;) {
+      const bool missing = lane == 0 && r > 0 && (rst >> 2) != epoch;
+      if(missing) Desc<A>::load(rdesc + (r - 1), rst, rval);
+      if(!__any_sync(SB_FULL_MASK, missing && (rst >> 2) != epoch)) break;
+      if(__any_sync(SB_FULL_MASK, dl.expired())) {
+        if(lane == 0) *err = 1u;
+        break;
+      }
     }
     total += sb::shfl_idx(rval, 0);
   }
@@ -220,7 +242,7 @@ template <typename A, int MODE, bool ALIGNED>
 __global__ void __launch_bounds__(SCAN_NT)
 scan_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
     const A* __restrict__ seed, typename Desc<A>::word* desc, unsigned long long* ticket, unsigned long long ticket_base,
-    uint32_t epoch, int use_lookback) {
+    uint32_t epoch, int use_lookback, unsigned* err, unsigned long long timeout_ns) {
   using C = TileCfg<A, SCAN_NT / 32, SCAN_K>;
   constexpr int VEC = C::VEC;
   constexpr int K = SCAN_K;
@@ -272,7 +294,8 @@ scan_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t
         if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | (tile_has_head ? ST_INCL : ST_AGG), tile_agg);
         const bool starts_on_head = MODE != MODE_PLAIN && (sb::shfl_idx(hf[0], 0) & 1u);
         if(!starts_on_head) {
-          p = lookback<A>(desc, tile, epoch);
+          Deadline dl(timeout_ns);
+          p = lookback<A>(desc, tile, epoch, dl, err);
           if(!tile_has_head && lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | ST_INCL, p + tile_agg);
         }
       }
@@ -295,7 +318,8 @@ __host__ __device__ constexpr int ws_stage_bytes() {
 template <typename A, int MODE, int K, int NW>
 __global__ void __launch_bounds__((NW + 2) * 32, SB_WS_MINB)
 scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
-    const A* __restrict__ seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, long long num_tiles, int flags_in_ring) {
+    const A* __restrict__ seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, long long num_tiles, int flags_in_ring,
+    unsigned* err, unsigned long long timeout_ns) {
   using C = TileCfg<A, NW, K>;
   constexpr int VEC = C::VEC;
   constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K, NW>();
@@ -369,7 +393,75 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
   } else if(warp == NW + 1) {
     // ===== look-back warp =====
     if(!use_lookback) return;
+    if(MODE == MODE_PLAIN && SB_WS_TOTALS) {
+      // Plain scans: round TOTALS instead of a chain of round prefixes.  The look-back warp of CTA 0 (the leader: position 0
+      // has a tile in every round) sums the G aggregates of a round as soon as they are out and publishes the total; every
+      // look-back warp keeps the prefix of its round as a running sum of those totals.  A total depends on nothing but phase
+      // A, so a late round no longer delays the rounds behind it the way the chained prefix (rdesc[r] needs rdesc[r-1]) did.
+      // Aggregates and totals are published AHEAD of the warp's own look-back, also from inside its polling loop: a
+      // descriptor must not wait for the prefix of the tile before it.  (Both ideas come from the multi-GPU kernel,
+      // sb_scan_cyclic.cu, where they lifted the one-GPU rate from 5.4-5.9 to 5.9-6.2 TB/s.)
+      Deadline dl(timeout_ns);
+      typename Desc<A>::word* rtot = desc + num_tiles;  // one total per round behind the tile descriptors
+      const bool leader = blockIdx.x == 0;
+      const long long pos = blockIdx.x;
+      const long long rounds = (num_tiles + G - 1) / G;
+      A E = A(0);
+      if(seed) E = *seed;
+      long long pa = 0, cur = 0;
+      auto publish = [&](long long must) {  // blocks until round `must` is out (-1: only what is ready)
+        while(pa < my_tiles) {
+          const int ls = (int)(pa % WS_NSLOT);
+          const uint32_t lp = (uint32_t)(pa / WS_NSLOT) & 1u;
+          if(pa <= must) {
+            mbar_wait(smem_u32(&agg_bar[ls]), lp);
+          } else {
+            if(pa > cur + WS_DEPTH) break;
+            if(!__all_sync(SB_FULL_MASK, mbar_test(smem_u32(&agg_bar[ls]), lp))) break;
+          }
+          A my_prefix, tile_agg;
+          bool my_open, tile_has_head;
+          combine_warps<A, MODE, NW>(s_wagg[ls], s_wflag[ls], -1, my_prefix, my_open, tile_agg, tile_has_head);
+          if(lane == 0) Desc<A>::store(desc + pos + pa * G, (epoch << 2) | ST_AGG, tile_agg);
+          if(leader && pa + 1 < rounds) {  // the last round's total has no reader
+            __syncwarp();
+            const A total = sum_round_aggregates<A>(desc + pa * G, (int)G, epoch, dl, err);
+            if(lane == 0) Desc<A>::store(rtot + pa, (epoch << 2) | ST_INCL, total);
+          }
+          ++pa;
+        }
+      };
+      for(long long i = 0; i < my_tiles; ++i) {
+        const int slot = (int)(i % WS_NSLOT);
+        cur = i;
+        publish(i);
+        uint32_t st = (epoch << 2) | ST_INCL;
+        A tv = A(0);
+        if(i > 0 && lane == 0) Desc<A>::load(rtot + (i - 1), st, tv);
+        const A local = sum_round_aggregates<A>(desc + i * G, (int)pos, epoch, dl, err);
+        for(;;) {
+          bool missing = false;
+          if(i > 0 && lane == 0 && (st >> 2) != epoch) {
+            Desc<A>::load(rtot + (i - 1), st, tv);
+            missing = (st >> 2) != epoch;
+          }
+          if(!__any_sync(SB_FULL_MASK, missing)) break;
+          publish(-1);
+          if(__any_sync(SB_FULL_MASK, dl.expired())) {
+            if(lane == 0) *err = 1u;
+            break;
+          }
+        }
+        E += sb::shfl_idx(tv, 0);
+        if(lane == 0) {
+          s_tprefix[slot] = E + local;
+          mbar_arrive(smem_u32(&prefix_bar[slot]));
+        }
+      }
+      return;
+    }
     const typename Desc<A>::word* rdesc = desc + num_tiles;  // one prefix per round behind the tile descriptors
+    Deadline dl_seg(timeout_ns);
     for(long long i = 0; i < my_tiles; ++i) {
       const int slot = (int)(i % WS_NSLOT);
       const long long tile = (long long)blockIdx.x + i * G;
@@ -387,7 +479,7 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
       // a lazy tile publishes a placeholder: its value is never used (see is_lazy), its presence is what pollers wait for
       if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | (tile_has_head ? ST_INCL : ST_AGG), tile_agg);
       A p = A(0);
-      if(!on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed);
+      if(!on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed, dl_seg, err);
       if(MODE == MODE_PLAIN && SB_WPREFIX) {
         (void)warp_prefixes<A, NW>(s_wagg[slot], s_wprefix[slot], p, true);
         __threadfence_block();  // every writing lane orders its s_wprefix store before the warp barrier; lane 0 then releases
@@ -701,8 +793,10 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
   }
   // Cooperative launch: the runtime guarantees that all CTAs of the grid are co-resident (or refuses the
   // launch) — the forward-progress condition of the static round-robin look-back.  No grid barrier is used.
+  unsigned* err = ctx->err_dev;
+  unsigned long long timeout_ns = sb_peer_timeout_ns();
   void* args[] = {(void*)&in, (void*)&out, (void*)&n, (void*)&exclusive, (void*)&seg_len, (void*)&seg_mask, (void*)&flags, (void*)&seed,
-      (void*)&desc, (void*)&epoch, (void*)&use_lookback, (void*)&num_tiles, (void*)&flags_in_ring};
+      (void*)&desc, (void*)&epoch, (void*)&use_lookback, (void*)&num_tiles, (void*)&flags_in_ring, (void*)&err, (void*)&timeout_ns};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_ws_kernel<A, MODE, K, NW>, dim3((unsigned)grid), dim3(WS_THREADS), args, smem, ctx->stream);
   if(e != cudaSuccess) return (int)e;
   return SB_OK;
@@ -783,7 +877,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   const dim3 grid((unsigned)tiles), block(SCAN_NT);
 #define SB_SCAN_LAUNCH(MODE_, AL_)                                                                                       \
   scan_kernel<A, MODE_, AL_><<<grid, block, 0, ctx->stream>>>(ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, \
-      desc, ctx->scan_ticket, tbase, epoch, use_lookback)
+      desc, ctx->scan_ticket, tbase, epoch, use_lookback, ctx->err_dev, sb_peer_timeout_ns())
   if(mode == MODE_PLAIN) {
     if(aligned) SB_SCAN_LAUNCH(MODE_PLAIN, true); else SB_SCAN_LAUNCH(MODE_PLAIN, false);
   } else if(mode == MODE_IMPLICIT) {

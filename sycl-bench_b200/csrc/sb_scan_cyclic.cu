@@ -66,45 +66,6 @@ struct PeerTable {
   unsigned long long* started[CY_MAX_WORLD];  // started[world] array of peer d
 };
 
-// Warp-collective: sum of the aggregates desc[0 .. count) of one round, in a fixed order (lane-strided partial sums,
-// then the xor tree), polling until every descriptor carries `epoch`.  All loads of a pass are issued back to back.
-template <typename A>
-__device__ __forceinline__ A sum_round_aggregates(const typename Desc<A>::word* row, int count, uint32_t epoch, Deadline& dl, unsigned* err) {
-  constexpr int U = 5;  // 5 x 32 descriptors per window: one window covers a round of 148 tiles
-  const int lane = sb::lane_id();
-  A lane_sum = A(0);
-  for(int lo = 0; lo < count; lo += 32 * U) {
-    uint32_t st[U];
-    A val[U];
-#pragma unroll
-    for(int u = 0; u < U; ++u) {
-      const int q = lo + u * 32 + lane;
-      st[u] = (epoch << 2) | ST_AGG;
-      val[u] = A(0);
-      if(q < count) Desc<A>::load(row + q, st[u], val[u]);
-    }
-    for(;;) {
-      bool missing = false;
-#pragma unroll
-      for(int u = 0; u < U; ++u) {
-        const int q = lo + u * 32 + lane;
-        if(q < count && (st[u] >> 2) != epoch) {
-          missing = true;
-          Desc<A>::load(row + q, st[u], val[u]);
-        }
-      }
-      if(!__any_sync(SB_FULL_MASK, missing)) break;
-      if(__any_sync(SB_FULL_MASK, dl.expired())) {
-        if(lane == 0) *err = 1u;
-        break;
-      }
-    }
-#pragma unroll
-    for(int u = 0; u < U; ++u) lane_sum += val[u];
-  }
-  return sb::warp_sum<A>(lane_sum);
-}
-
 // phase B: the warp's K rows of a FULL tile, global (L2-resident) -> registers, one 128-bit load per lane and row
 template <typename A, int K>
 __device__ __forceinline__ void tile_load_l2(A (&v)[K][16 / sizeof(A)], const A* lane_ptr, int hint, unsigned long long policy) {

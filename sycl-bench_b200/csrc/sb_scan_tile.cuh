@@ -2,6 +2,7 @@
 // descriptors, mbarrier / TMA bulk-copy primitives and the per-warp row scans.  See sb_scan.cu for the design.
 #pragma once
 #include "sb_common.cuh"
+#include "sb_peer.cuh"
 
 namespace sbscan {
 
@@ -450,6 +451,46 @@ __device__ __forceinline__ void combine_warps(const A* wagg, const int* wflag, i
   }
   tile_agg = run;
   tile_has_head = !run_open;
+}
+
+// ---- polling helpers shared by the look-back warps -------------------------------------------------------------
+// Warp-collective: sum of the aggregates desc[0 .. count) of one round, in a fixed order (lane-strided partial sums,
+// then the xor tree), polling until every descriptor carries `epoch`.  All loads of a pass are issued back to back.
+template <typename A>
+__device__ __forceinline__ A sum_round_aggregates(const typename Desc<A>::word* row, int count, uint32_t epoch, Deadline& dl, unsigned* err) {
+  constexpr int U = 5;  // 5 x 32 descriptors per window: one window covers a round of 148 tiles
+  const int lane = sb::lane_id();
+  A lane_sum = A(0);
+  for(int lo = 0; lo < count; lo += 32 * U) {
+    uint32_t st[U];
+    A val[U];
+#pragma unroll
+    for(int u = 0; u < U; ++u) {
+      const int q = lo + u * 32 + lane;
+      st[u] = (epoch << 2) | ST_AGG;
+      val[u] = A(0);
+      if(q < count) Desc<A>::load(row + q, st[u], val[u]);
+    }
+    for(;;) {
+      bool missing = false;
+#pragma unroll
+      for(int u = 0; u < U; ++u) {
+        const int q = lo + u * 32 + lane;
+        if(q < count && (st[u] >> 2) != epoch) {
+          missing = true;
+          Desc<A>::load(row + q, st[u], val[u]);
+        }
+      }
+      if(!__any_sync(SB_FULL_MASK, missing)) break;
+      if(__any_sync(SB_FULL_MASK, dl.expired())) {
+        if(lane == 0) *err = 1u;
+        break;
+      }
+    }
+#pragma unroll
+    for(int u = 0; u < U; ++u) lane_sum += val[u];
+  }
+  return sb::warp_sum<A>(lane_sum);
 }
 
 }  // namespace sbscan
