@@ -100,10 +100,10 @@ constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
 #ifndef SB_WPREFIX
 #define SB_WPREFIX 0
 #endif
-//   SB_WS_TOTALS  plain look-back scans: independent round totals + publish-ahead instead of the chained round prefix
-#ifndef SB_WS_TOTALS
-#define SB_WS_TOTALS 1
-#endif
+// Also measured and NOT kept (profiles/r02_ops_v8_totals_ab.jsonl): the two-phase kernel's scheme — independent round totals
+// summed by a leader + aggregates published ahead of the look-back — transplanted into this kernel, where the tile waits in
+// shared memory and phase A is only ONE tile ahead: 5.7-5.9 TB/s against 6.26-6.33 for the chained round prefix below.  The
+// extra hop (aggregate -> leader -> total -> every look-back warp) does not fit into one round of look-ahead.
 #ifndef SB_EXCL_T
 #define SB_EXCL_T 1
 #endif
@@ -393,73 +393,6 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
   } else if(warp == NW + 1) {
     // ===== look-back warp =====
     if(!use_lookback) return;
-    if(MODE == MODE_PLAIN && SB_WS_TOTALS) {
-      // Plain scans: round TOTALS instead of a chain of round prefixes.  The look-back warp of CTA 0 (the leader: position 0
-      // has a tile in every round) sums the G aggregates of a round as soon as they are out and publishes the total; every
-      // look-back warp keeps the prefix of its round as a running sum of those totals.  A total depends on nothing but phase
-      // A, so a late round no longer delays the rounds behind it the way the chained prefix (rdesc[r] needs rdesc[r-1]) did.
-      // Aggregates and totals are published AHEAD of the warp's own look-back, also from inside its polling loop: a
-      // descriptor must not wait for the prefix of the tile before it.  (Both ideas come from the multi-GPU kernel,
-      // sb_scan_cyclic.cu, where they lifted the one-GPU rate from 5.4-5.9 to 5.9-6.2 TB/s.)
-      Deadline dl(timeout_ns);
-      typename Desc<A>::word* rtot = desc + num_tiles;  // one total per round behind the tile descriptors
-      const bool leader = blockIdx.x == 0;
-      const long long pos = blockIdx.x;
-      const long long rounds = (num_tiles + G - 1) / G;
-      A E = A(0);
-      if(seed) E = *seed;
-      long long pa = 0, cur = 0;
-      auto publish = [&](long long must) {  // blocks until round `must` is out (-1: only what is ready)
-        while(pa < my_tiles) {
-          const int ls = (int)(pa % WS_NSLOT);
-          const uint32_t lp = (uint32_t)(pa / WS_NSLOT) & 1u;
-          if(pa <= must) {
-            mbar_wait(smem_u32(&agg_bar[ls]), lp);
-          } else {
-            if(pa > cur + WS_DEPTH) break;
-            if(!__all_sync(SB_FULL_MASK, mbar_test(smem_u32(&agg_bar[ls]), lp))) break;
-          }
-          A my_prefix, tile_agg;
-          bool my_open, tile_has_head;
-          combine_warps<A, MODE, NW>(s_wagg[ls], s_wflag[ls], -1, my_prefix, my_open, tile_agg, tile_has_head);
-          if(lane == 0) Desc<A>::store(desc + pos + pa * G, (epoch << 2) | ST_AGG, tile_agg);
-          if(leader && pa + 1 < rounds) {  // the last round's total has no reader
-            __syncwarp();
-            const A total = sum_round_aggregates<A>(desc + pa * G, (int)G, epoch, dl, err);
-            if(lane == 0) Desc<A>::store(rtot + pa, (epoch << 2) | ST_INCL, total);
-          }
-          ++pa;
-        }
-      };
-      for(long long i = 0; i < my_tiles; ++i) {
-        const int slot = (int)(i % WS_NSLOT);
-        cur = i;
-        publish(i);
-        uint32_t st = (epoch << 2) | ST_INCL;
-        A tv = A(0);
-        if(i > 0 && lane == 0) Desc<A>::load(rtot + (i - 1), st, tv);
-        const A local = sum_round_aggregates<A>(desc + i * G, (int)pos, epoch, dl, err);
-        for(;;) {
-          bool missing = false;
-          if(i > 0 && lane == 0 && (st >> 2) != epoch) {
-            Desc<A>::load(rtot + (i - 1), st, tv);
-            missing = (st >> 2) != epoch;
-          }
-          if(!__any_sync(SB_FULL_MASK, missing)) break;
-          publish(-1);
-          if(__any_sync(SB_FULL_MASK, dl.expired())) {
-            if(lane == 0) *err = 1u;
-            break;
-          }
-        }
-        E += sb::shfl_idx(tv, 0);
-        if(lane == 0) {
-          s_tprefix[slot] = E + local;
-          mbar_arrive(smem_u32(&prefix_bar[slot]));
-        }
-      }
-      return;
-    }
     const typename Desc<A>::word* rdesc = desc + num_tiles;  // one prefix per round behind the tile descriptors
     Deadline dl_seg(timeout_ns);
     for(long long i = 0; i < my_tiles; ++i) {
