@@ -90,22 +90,16 @@ constexpr int WS_NW_NARROW = SB_WS_NW_NARROW;
 #define SB_WS_NW_FLAGS SB_WS_NW  // worker warps of the explicit-flag instantiation
 #endif
 constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
-// A/B switches of two instruction-count optimisations of the plain look-back scan, measured at 2^28
-// (profiles/r02_ops_v6_wprefix_ab.jsonl):
-//   SB_EXCL_T  exclusive flag resolved at compile time in pass 2 (no 64-bit select per element): +1..2 %, ON.
-//   SB_WPREFIX per-warp prefixes computed once by the look-back warp instead of every worker lane walking the NW warp
-//              sums: 15 % fewer worker instructions for 64-bit types, but the two extra warp scans sit on the inter-CTA
-//              hand-over (aggregate -> descriptor, prefix -> workers) and the kernel LOSES 10-17 % (i32 6.30 -> 5.17,
-//              i64 6.18 -> 5.56 TB/s).  OFF: the chain, not the issue slots, bounds this kernel.
-#ifndef SB_WPREFIX
-#define SB_WPREFIX 0
-#endif
-// Also measured and NOT kept (profiles/r02_ops_v8_totals_ab.jsonl): the two-phase kernel's scheme — independent round totals
-// summed by a leader + aggregates published ahead of the look-back — transplanted into this kernel, where the tile waits in
-// shared memory and phase A is only ONE tile ahead: 5.7-5.9 TB/s against 6.26-6.33 for the chained round prefix below.  The
-// extra hop (aggregate -> leader -> total -> every look-back warp) does not fit into one round of look-ahead.
-#ifndef SB_EXCL_T
-#define SB_EXCL_T 1
+// Measured and NOT kept for this kernel (profiles/r02_ops_v6_wprefix_ab.jsonl, r02_ops_v8_totals_ab.jsonl):
+//  * per-warp prefixes computed once by the look-back warp instead of every worker lane walking the NW warp sums: 15 % fewer
+//    worker instructions for 64-bit types, but the two extra warp scans sit on the inter-CTA hand-over (aggregate ->
+//    descriptor, prefix -> workers) and the kernel LOSES 10-17 % (i32 6.30 -> 5.17, i64 6.18 -> 5.56 TB/s);
+//  * the two-phase kernel's independent round totals (leader sums a round, every look-back warp keeps a running sum) instead
+//    of the chained round prefix: 5.7-5.9 against 6.26-6.33 TB/s — with the tile waiting in shared memory phase A is only ONE
+//    tile ahead, and the extra hop (aggregate -> leader -> total -> look-back) does not fit into one round of look-ahead.
+// Both say the same: the hand-over chain, not the issue slots, bounds this kernel.
+#ifndef SB_WS_PUBLISH_AHEAD
+#define SB_WS_PUBLISH_AHEAD 1  // tile descriptors are published ahead of the warp's own look-back (A/B: 0)
 #endif
 #ifndef SB_WS_NW_LB64
 #define SB_WS_NW_LB64 14  // 64-bit types, segmented modes with look-back: 14 + 2 = 16 warps -> 128 registers per thread
@@ -157,9 +151,9 @@ __device__ __forceinline__ A lookback(const typename Desc<A>::word* desc, long l
 }
 
 // round look-back (persistent kernel), see the header comment
-template <typename A, int MODE>
+template <typename A, int MODE, typename Idle>
 __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, const typename Desc<A>::word* rdesc, long long tile,
-    long long G, uint32_t epoch, const A* __restrict__ seed, Deadline& dl, unsigned* err) {
+    long long G, uint32_t epoch, const A* __restrict__ seed, Deadline& dl, unsigned* err, Idle on_idle) {
   constexpr int U = SCAN_WINDOW;
   const int lane = sb::lane_id();
   const long long r = tile / G;
@@ -201,6 +195,7 @@ __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, 
       }
       if(lane == 0 && r > 0 && (rst >> 2) != epoch) Desc<A>::load(rdesc + (r - 1), rst, rval);  // keep the round prefix polling too
       if(!__any_sync(SB_FULL_MASK, missing)) break;
+      on_idle();  // (publishes this CTA's next aggregate if its phase A has finished meanwhile)
       if(__any_sync(SB_FULL_MASK, dl.expired())) {
         if(lane == 0) *err = 1u;
         break;
@@ -227,6 +222,7 @@ __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, 
       const bool missing = lane == 0 && r > 0 && (rst >> 2) != epoch;
       if(missing) Desc<A>::load(rdesc + (r - 1), rst, rval);
       if(!__any_sync(SB_FULL_MASK, missing && (rst >> 2) != epoch)) break;
+      on_idle();
       if(__any_sync(SB_FULL_MASK, dl.expired())) {
         if(lane == 0) *err = 1u;
         break;
@@ -328,7 +324,8 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
   __shared__ A s_wagg[WS_NSLOT][NW];
   __shared__ int s_wflag[WS_NSLOT][NW];
   __shared__ A s_tprefix[WS_NSLOT];
-  __shared__ A s_wprefix[WS_NSLOT][NW];  // plain scans: per-warp prefixes written by the look-back warp (tile prefix included)
+  __shared__ A s_tagg[WS_NSLOT];    // look-back warp, lane 0: aggregate / has-head of the tiles it has published
+  __shared__ int s_thead[WS_NSLOT];
   __shared__ __align__(8) unsigned long long xchg_bar;  // workers' barrier of "lazy" tiles (below)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -395,32 +392,50 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
     if(!use_lookback) return;
     const typename Desc<A>::word* rdesc = desc + num_tiles;  // one prefix per round behind the tile descriptors
     Deadline dl_seg(timeout_ns);
+    // The tile descriptor is published AHEAD of the warp's own look-back: as soon as phase A of a tile is complete (at most
+    // WS_DEPTH tiles ahead), also from inside the look-back's polling loop.  Publishing tile i+1 only after the look-back of
+    // tile i made every descriptor wait for a prefix (measured on the two-phase kernel, sb_scan_cyclic.cu: +10 % on one GPU).
+    long long pa = 0, cur = 0;
+    auto publish = [&](long long must) {  // blocks until tile `must` of this CTA is out (-1: only what is ready)
+      while(pa < my_tiles) {
+        const int ls = (int)(pa % WS_NSLOT);
+        const uint32_t lp = (uint32_t)(pa / WS_NSLOT) & 1u;
+        if(pa <= must) {
+          mbar_wait(smem_u32(&agg_bar[ls]), lp);
+        } else {
+          if(!SB_WS_PUBLISH_AHEAD || pa > cur + WS_DEPTH) break;
+          if(!__all_sync(SB_FULL_MASK, mbar_test(smem_u32(&agg_bar[ls]), lp))) break;
+        }
+        const long long t = (long long)blockIdx.x + pa * G;
+        A tile_agg = A(0);
+        bool tile_has_head = false;
+        if(!is_lazy(t)) {
+          A my_prefix;
+          bool my_open;
+          combine_warps<A, MODE, NW>(s_wagg[ls], s_wflag[ls], -1, my_prefix, my_open, tile_agg, tile_has_head);
+        }
+        // a lazy tile publishes a placeholder: its value is never used (see is_lazy), its presence is what pollers wait for
+        if(lane == 0) {
+          Desc<A>::store(desc + t, (epoch << 2) | (tile_has_head ? ST_INCL : ST_AGG), tile_agg);
+          s_tagg[ls] = tile_agg;
+          s_thead[ls] = tile_has_head ? 1 : 0;
+        }
+        ++pa;
+      }
+    };
     for(long long i = 0; i < my_tiles; ++i) {
       const int slot = (int)(i % WS_NSLOT);
       const long long tile = (long long)blockIdx.x + i * G;
-      const bool on_head = starts_on_head(tile), lazy = is_lazy(tile);  // (the flag-byte loads fly during the wait)
-      mbar_wait(smem_u32(&agg_bar[slot]), (uint32_t)(i / WS_NSLOT) & 1u);
-      A tile_agg = A(0);
-      bool tile_has_head = false;
-      if(MODE == MODE_PLAIN && SB_WPREFIX) {
-        tile_agg = warp_prefixes<A, NW>(s_wagg[slot], nullptr, A(0), false);
-      } else if(!lazy) {
-        A my_prefix;
-        bool my_open;
-        combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], -1, my_prefix, my_open, tile_agg, tile_has_head);
-      }
-      // a lazy tile publishes a placeholder: its value is never used (see is_lazy), its presence is what pollers wait for
-      if(lane == 0) Desc<A>::store(desc + tile, (epoch << 2) | (tile_has_head ? ST_INCL : ST_AGG), tile_agg);
+      const bool on_head = starts_on_head(tile);  // (the flag-byte load flies during the wait)
+      cur = i;
+      publish(i);
       A p = A(0);
-      if(!on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed, dl_seg, err);
-      if(MODE == MODE_PLAIN && SB_WPREFIX) {
-        (void)warp_prefixes<A, NW>(s_wagg[slot], s_wprefix[slot], p, true);
-        __threadfence_block();  // every writing lane orders its s_wprefix store before the warp barrier; lane 0 then releases
-        __syncwarp();
-      }
+      if(!on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed, dl_seg, err, [&] { publish(-1); });
       if(lane == 0) {
-        if((tile + 1) % G == 0)
-          Desc<A>::store(const_cast<typename Desc<A>::word*>(rdesc) + tile / G, (epoch << 2) | ST_INCL, tile_has_head ? tile_agg : p + tile_agg);
+        if((tile + 1) % G == 0) {
+          const A tile_agg = s_tagg[slot];  // written by this lane in publish()
+          Desc<A>::store(const_cast<typename Desc<A>::word*>(rdesc) + tile / G, (epoch << 2) | ST_INCL, s_thead[slot] ? tile_agg : p + tile_agg);
+        }
         s_tprefix[slot] = p;
         mbar_arrive(smem_u32(&prefix_bar[slot]));
       }
@@ -548,18 +563,13 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         } else {
           mbar_wait(smem_u32(&agg_bar[slot]), par);
         }
-        if(MODE == MODE_PLAIN && use_lookback && (SB_WPREFIX || SB_EXCL_T)) {
-          A warp_prefix;
-          if(SB_WPREFIX) {
-            warp_prefix = s_wprefix[slot][warp];
-          } else {
-            A my_prefix, tile_agg;
-            bool my_open, tile_has_head;
-            combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], warp, my_prefix, my_open, tile_agg, tile_has_head);
-            warp_prefix = my_prefix + tile_prefix;
-          }
-          if(!SB_EXCL_T) tile_pass2_store<A, MODE, true, K>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, exclusive);
-          else if(exclusive) tile_pass2_store<A, MODE, true, K, false, 1>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, 1);
+        if(MODE == MODE_PLAIN && use_lookback) {
+          A my_prefix, tile_agg;
+          bool my_open, tile_has_head;
+          combine_warps<A, MODE, NW>(s_wagg[slot], s_wflag[slot], warp, my_prefix, my_open, tile_agg, tile_has_head);
+          const A warp_prefix = my_prefix + tile_prefix;
+          // exclusive flag resolved at compile time: no 64-bit select per element (+1-2 %)
+          if(exclusive) tile_pass2_store<A, MODE, true, K, false, 1>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, 1);
           else tile_pass2_store<A, MODE, true, K, false, 0>(v, hf, carry_in, open, warp_prefix, wbase, full_tile, n, out, 0);
         } else {
           A my_prefix, tile_agg;

@@ -408,26 +408,6 @@ __device__ __forceinline__ void tile_pass2_store(const A (&v)[K][16 / sizeof(A)]
   }
 }
 
-// Plain scans: one warp turns the NW per-warp sums of a tile into per-warp PREFIXES (tile prefix included), so that a
-// worker reads one value instead of walking all NW sums with selects (combine_warps below: 18 x (LDS, add, 2-4 SEL)
-// per lane and tile).  Returns the tile aggregate.  wprefix[w] = tile_prefix + sum of wagg[0..w).
-template <typename A, int NW>
-__device__ __forceinline__ A warp_prefixes(const A* wagg, A* wprefix, A tile_prefix, bool write) {
-  static_assert(NW <= 32, "one lane per worker warp");
-  const int lane = threadIdx.x & 31;
-  const A mine = lane < NW ? wagg[lane] : A(0);
-  A incl = mine;
-#pragma unroll
-  for(int d = 1; d < 32; d <<= 1) {
-    const A up = sb::shfl_up(incl, d);
-    if(lane >= d) incl += up;
-  }
-  A excl = sb::shfl_up(incl, 1);
-  if(lane == 0) excl = A(0);
-  if(write && lane < NW) wprefix[lane] = tile_prefix + excl;
-  return sb::shfl_idx(incl, 31);
-}
-
 // prefix of the warps in front of `warp` inside a tile and the tile's own (aggregate, has-head)
 template <typename A, int MODE, int NW>
 __device__ __forceinline__ void combine_warps(const A* wagg, const int* wflag, int warp, A& my_prefix, bool& my_open, A& tile_agg,
