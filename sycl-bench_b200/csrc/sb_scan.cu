@@ -98,8 +98,11 @@ constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
 //    of the chained round prefix: 5.7-5.9 against 6.26-6.33 TB/s — with the tile waiting in shared memory phase A is only ONE
 //    tile ahead, and the extra hop (aggregate -> leader -> total -> look-back) does not fit into one round of look-ahead.
 // Both say the same: the hand-over chain, not the issue slots, bounds this kernel.
+//  * tile descriptors published ahead of the warp's own look-back (what lifted the two-phase kernel by 10 %): neutral here
+//    (2^28: i32 6.34 / 6.34, i64 6.08 / 6.24; 2^30: 6.59 / 6.48 TB/s with / without, profiles/r02_ops_v9_publish_ahead_ab.jsonl) —
+//    phase A is one tile ahead, there is next to nothing to publish early.  Off; -DSB_WS_PUBLISH_AHEAD=1 builds it.
 #ifndef SB_WS_PUBLISH_AHEAD
-#define SB_WS_PUBLISH_AHEAD 1  // tile descriptors are published ahead of the warp's own look-back (A/B: 0)
+#define SB_WS_PUBLISH_AHEAD 0
 #endif
 #ifndef SB_WS_NW_LB64
 #define SB_WS_NW_LB64 14  // 64-bit types, segmented modes with look-back: 14 + 2 = 16 warps -> 128 registers per thread
@@ -392,9 +395,8 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
     if(!use_lookback) return;
     const typename Desc<A>::word* rdesc = desc + num_tiles;  // one prefix per round behind the tile descriptors
     Deadline dl_seg(timeout_ns);
-    // The tile descriptor is published AHEAD of the warp's own look-back: as soon as phase A of a tile is complete (at most
-    // WS_DEPTH tiles ahead), also from inside the look-back's polling loop.  Publishing tile i+1 only after the look-back of
-    // tile i made every descriptor wait for a prefix (measured on the two-phase kernel, sb_scan_cyclic.cu: +10 % on one GPU).
+    // publish(must): tile aggregate -> descriptor, for the tiles of this CTA up to `must` (with SB_WS_PUBLISH_AHEAD also for a
+    // tile whose phase A has already finished, from inside the look-back's polling loop; see the note at the macro).
     long long pa = 0, cur = 0;
     auto publish = [&](long long must) {  // blocks until tile `must` of this CTA is out (-1: only what is ready)
       while(pa < my_tiles) {
