@@ -10,4 +10,5 @@ for path in sys.argv[1:]:
         except Exception:
             print(l.rstrip())
             continue
-        print(f"{r['lib']:30s} {r['op']:18s} {r['dtype']} {r['ms_min']:8.4f} ms {r['GBps_min']:8.1f} GB/s (med {r['GBps_med']:.1f})")
+        env = " ".join(f"{k}={v}" for k, v in sorted(r.get("env", {}).items()) if k != "SB_CUDA_LIB")
+        print(f"{r['lib']:30s} {env:22s} {r['op']:18s} {r['dtype']} {r['ms_min']:8.4f} ms {r['GBps_min']:8.1f} GB/s (med {r['GBps_med']:.1f})")

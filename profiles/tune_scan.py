@@ -24,8 +24,8 @@ def worker(args):
     pkg = ge.load_package()
     torch.cuda.set_device(0)
     ctx = pkg.Context(0, torch.cuda.current_stream().cuda_stream)
-    tdt = {"i32": torch.int32, "i64": torch.int64, "f32": torch.float32, "f64": torch.float64}
-    size = {"i32": 4, "i64": 8, "f32": 4, "f64": 8}
+    tdt = {"i16": torch.int16, "i32": torch.int32, "i64": torch.int64, "f32": torch.float32, "f64": torch.float64}
+    size = {"i16": 2, "i32": 4, "i64": 8, "f32": 4, "f64": 8}
     n = 1 << args.log2n
     res = []
     for t in args.dtypes.split(","):
@@ -33,7 +33,12 @@ def worker(args):
         y = torch.empty_like(x)
         out = torch.zeros(1, dtype=tdt[t], device="cuda")
         ctx.iota(x)
-        cases = {
+        if t == "i16":  # the C ABI has int16 for the segmented reduction only
+            cases = {}
+            for L in (64, 128, 256, 1024):
+                cases[f"segreduce{L}"] = ((lambda L=L: ctx.segreduce(y, L)), n * 2 + n // L * 2)
+        else:
+            cases = {
             "reduce": (lambda: ctx.reduce(x, out), n * size[t]),
             "scan": (lambda: ctx.scan(x, y), 2 * n * size[t]),
             "scan_cyclic": (lambda: ctx.scan_cyclic(x, y), 2 * n * size[t]),
@@ -41,14 +46,18 @@ def worker(args):
             "segscan_L65536": (lambda: ctx.segscan(x, y, seg_len=65536), 2 * n * size[t]),
             "segreduce256": (lambda: ctx.segreduce(y, 256), n * size[t] + n // 256 * size[t]),
             "segreduce64": (lambda: ctx.segreduce(y, 64), n * size[t] + n // 64 * size[t]),
+            "segreduce128": (lambda: ctx.segreduce(y, 128), n * size[t] + n // 128 * size[t]),
             "segreduce1024": (lambda: ctx.segreduce(y, 1024), n * size[t] + n // 1024 * size[t]),
             "carry_add": (lambda: ctx.carry_add(y, out), 2 * n * size[t]),
             "iota": (lambda: ctx.iota(y), n * size[t]),
         }
-        if args.flags:
+        if args.flags and t != "i16":
             fl = torch.zeros(n, dtype=torch.uint8, device="cuda")
             fl[::256] = 1
             cases["segscan_flags256"] = (lambda: ctx.segscan(x, y, head_flags=fl), 2 * n * size[t] + n)
+            # heads at random positions, mean segment length 256: no tile starts on a head
+            fr = (torch.rand(n, device="cuda") < 1.0 / 256).to(torch.uint8)
+            cases["segscan_flagsrand"] = (lambda: ctx.segscan(x, y, head_flags=fr), 2 * n * size[t] + n)
         for name in args.ops.split(","):
             if name not in cases:
                 continue

@@ -318,12 +318,13 @@ template <typename A, int MODE, int K, int NW>
 __global__ void __launch_bounds__((NW + 2) * 32, SB_WS_MINB)
 scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
     const A* __restrict__ seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, long long num_tiles, int flags_in_ring,
-    unsigned* err, unsigned long long timeout_ns) {
+    unsigned* err, unsigned long long timeout_ns, const unsigned* gate, unsigned gate_want) {
   using C = TileCfg<A, NW, K>;
   constexpr int VEC = C::VEC;
   constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K, NW>();
   extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x STAGE_BYTES
   __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES], agg_bar[WS_NSLOT], prefix_bar[WS_NSLOT];
+  if(gate && *gate != gate_want) return;  // explicit flags: the other kernel of the pair runs (flags_tile_heads_kernel)
   __shared__ A s_wagg[WS_NSLOT][NW];
   __shared__ int s_wflag[WS_NSLOT][NW];
   __shared__ A s_tprefix[WS_NSLOT];
@@ -599,12 +600,18 @@ constexpr int WS_TILE_IDS = 8;  // ring of tile ids handed from the producer to 
 template <typename A, int MODE, int K, int NW>
 __global__ void __launch_bounds__((NW + 1) * 32, SB_WS_MINB)
 scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
-    long long num_tiles, int flags_in_ring, unsigned long long* ticket, unsigned long long ticket_base) {
+    long long num_tiles, int flags_in_ring, unsigned long long* ticket, unsigned long long ticket_base, const unsigned* gate,
+    unsigned gate_want) {
   using C = TileCfg<A, NW, K>;
   constexpr int VEC = C::VEC;
   constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K, NW>();
   extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x STAGE_BYTES
   __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES], agg_bar[WS_NSLOT];
+  if(gate && *gate != gate_want) {
+    // not this kernel's case.  The host has already counted this launch's tickets (tiles + grid): draw them
+    if(threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(ticket, (unsigned long long)num_tiles + gridDim.x);
+    return;
+  }
   __shared__ A s_wagg[WS_NSLOT][NW];
   __shared__ int s_wflag[WS_NSLOT][NW];
   __shared__ int s_tile_id[WS_TILE_IDS];  // tile of the CTA's i-th iteration, -1 = no more tiles
@@ -686,6 +693,19 @@ scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg
   }
 }
 
+// ---- explicit head flags: does every tile start on a head? ----------------------------------------------------------
+// If so (the benchmark's own flags: a head every `--local` elements, and the tile is a multiple of that) no tile needs
+// anything from another tile and the independent-tile kernel does the job without descriptors, look-back warp and phase A.
+// The host cannot know without a round trip, so it launches this check (one byte per tile: ~3 us for 2^28 elements), then
+// BOTH scan kernels, each of which leaves at once unless the verdict in `gate` names it.
+__global__ void __launch_bounds__(1024) flags_tile_heads_kernel(const uint8_t* __restrict__ flags, long long num_tiles, size_t tile,
+    unsigned* gate) {
+  int ok = 1;
+  for(long long t = 1 + (long long)threadIdx.x; t < num_tiles; t += blockDim.x) ok &= __ldg(flags + (size_t)t * tile) != 0 ? 1 : 0;
+  ok = __syncthreads_and(ok);
+  if(threadIdx.x == 0) *gate = ok ? 1u : 0u;
+}
+
 // co-resident CTAs per SM of a persistent kernel instantiation.  The shared-memory opt-in is a per-device
 // function attribute, so the query (and the opt-in) is made once per device, on the current device.
 constexpr int SB_MAX_DEVICES = 64;
@@ -711,7 +731,8 @@ template <int MODE> struct ws_rows { static constexpr int K = MODE == MODE_FLAGS
 
 template <typename A, int MODE, int NW>
 int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* flags,
-    const A* seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, size_t tiles) {
+    const A* seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, size_t tiles, const unsigned* gate = nullptr,
+    unsigned gate_want = 0) {
   constexpr int K = ws_rows<MODE>::K;
   constexpr size_t smem = (size_t)WS_STAGES * ws_stage_bytes<A, MODE, K, NW>();
   constexpr int WS_THREADS = (NW + 2) * 32;
@@ -731,7 +752,7 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
     // (the host mirror of the ticket advances only once the launch is known to have been accepted)
     const unsigned long long tbase = ctx->scan_ticket_base;
     scan_independent_kernel<A, MODE, K, NW><<<(unsigned)g, (NW + 1) * 32, smem, ctx->stream>>>(in, out, n, exclusive, seg_len, seg_mask, flags,
-        num_tiles, flags_in_ring, ctx->scan_ticket, tbase);
+        num_tiles, flags_in_ring, ctx->scan_ticket, tbase, gate, gate_want);
     if(cudaError_t e = cudaGetLastError(); e != cudaSuccess) return (int)e;
     ctx->scan_ticket_base += tiles + g;
     return SB_OK;
@@ -741,7 +762,8 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
   unsigned* err = ctx->err_dev;
   unsigned long long timeout_ns = sb_peer_timeout_ns();
   void* args[] = {(void*)&in, (void*)&out, (void*)&n, (void*)&exclusive, (void*)&seg_len, (void*)&seg_mask, (void*)&flags, (void*)&seed,
-      (void*)&desc, (void*)&epoch, (void*)&use_lookback, (void*)&num_tiles, (void*)&flags_in_ring, (void*)&err, (void*)&timeout_ns};
+      (void*)&desc, (void*)&epoch, (void*)&use_lookback, (void*)&num_tiles, (void*)&flags_in_ring, (void*)&err, (void*)&timeout_ns,
+      (void*)&gate, (void*)&gate_want};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_ws_kernel<A, MODE, K, NW>, dim3((unsigned)grid), dim3(WS_THREADS), args, smem, ctx->stream);
   if(e != cudaSuccess) return (int)e;
   return SB_OK;
@@ -813,8 +835,24 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
     else if(mode == MODE_IMPLICIT && narrow) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_NARROW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && lb64) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT) rc = launch_ws<A, MODE_IMPLICIT, WS_NW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
-    else if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
-    else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else {
+      // explicit flags: check kernel + both scan kernels, gated by its verdict (see flags_tile_heads_kernel).
+      // SB_SCAN_FLAGS_GATE=0 launches the look-back kernel alone (A/B measurements).
+      static const bool gate_enabled = !(getenv("SB_SCAN_FLAGS_GATE") && getenv("SB_SCAN_FLAGS_GATE")[0] == '0');
+      const unsigned* gate = nullptr;
+      rc = SB_OK;
+      if(gate_enabled && use_lookback && tiles >= 64) {
+        unsigned* g = reinterpret_cast<unsigned*>(ctx->scan_ticket + 16);  // byte 128 of the ctx's 256-byte ticket block
+        flags_tile_heads_kernel<<<1, 1024, 0, ctx->stream>>>(flags, (long long)tiles, tile, g);
+        gate = g;
+        if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, 1u);
+        else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, 1u);
+      }
+      if(rc == SB_OK) {
+        if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles, gate, 0u);
+        else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles, gate, 0u);
+      }
+    }
     if(rc != SB_OK) return rc;
     SB_CHECK_LAUNCH(ctx);
     return SB_OK;

@@ -179,7 +179,11 @@ __global__ void __launch_bounds__(NT) segreduce_rows_kernel(A* buf, size_t n) {
 // warps [0, SRR_NW): workers, each owns 8 consecutive rows (two super-rows) of a tile; warp SRR_NW: producer.
 constexpr int SRR_NW = 16, SRR_STAGES = 3, SRR_TILE_BYTES = SRR_NW * 8 * 512, SRR_IDS = 8;
 
-template <typename A, int SHAPE>
+// LANE (segments of 128 / 256 / 512 bytes = SHAPE 8 / 16 / 32): a lane owns 128 CONTIGUOUS bytes of the tile instead of 16 bytes
+// of each of 8 rows, i.e. a whole segment or a half / quarter of one: 8 LDS.128 (chunk order rotated by the lane number, so the
+// eight lanes of a quarter-warp hit eight different 16-byte bank groups), a serial sum in registers, log2(SHAPE / 8) xor-shuffles
+// instead of log2(SHAPE) per row, and one head store per segment for the whole 4 KB of the warp.
+template <typename A, int SHAPE, bool LANE>
 __global__ void __launch_bounds__((SRR_NW + 1) * 32, 1)
 segreduce_ring_kernel(A* buf, size_t n, long long num_tiles, unsigned long long* ticket, unsigned long long ticket_base) {
   using namespace sbscan;
@@ -227,7 +231,33 @@ segreduce_ring_kernel(A* buf, size_t n, long long num_tiles, unsigned long long*
     const long long tile = s_tile_id[it % SRR_IDS];
     if(tile < 0) break;
     const size_t base = (size_t)tile * TILE + (size_t)warp * 2 * SUPER;  // first element of the warp's two super-rows
-    if((size_t)(tile + 1) * TILE <= n) {
+    if(LANE && (size_t)(tile + 1) * TILE <= n) {
+      using Acc = typename acc_of<A>::type;
+      constexpr int LPS = SHAPE / 8;  // lanes per segment
+      const unsigned char* sp = ring + (size_t)stage * SRR_TILE_BYTES + (size_t)threadIdx.x * 128;
+      sb::Vec<A> t[8];
+#pragma unroll
+      for(int k = 0; k < 8; ++k) t[k] = *reinterpret_cast<const sb::Vec<A>*>(sp + ((k + lane) & 7) * 16);
+      __syncwarp();
+      if(lane == 0) mbar_arrive(smem_u32(&empty_bar[stage]));  // the bytes live in registers now
+      Acc acc[VEC];
+#pragma unroll
+      for(int c = 0; c < VEC; ++c) acc[c] = (Acc)t[0].v[c];
+#pragma unroll
+      for(int k = 1; k < 8; ++k) {
+#pragma unroll
+        for(int c = 0; c < VEC; ++c) acc[c] += (Acc)t[k].v[c];
+      }
+#pragma unroll
+      for(int w = VEC / 2; w > 0; w >>= 1) {
+#pragma unroll
+        for(int c = 0; c < w; ++c) acc[c] += acc[c + w];
+      }
+      Acc r = acc[0];
+#pragma unroll
+      for(int d = LPS >> 1; d > 0; d >>= 1) r += __shfl_xor_sync(SB_FULL_MASK, r, d);
+      if((lane & (LPS - 1)) == 0) buf[(size_t)tile * TILE + (size_t)threadIdx.x * (128 / sizeof(A))] = (A)r;
+    } else if((size_t)(tile + 1) * TILE <= n) {
       sb::Vec<A> t0[4], t1[4];
       const unsigned char* sp = ring + (size_t)stage * SRR_TILE_BYTES + (size_t)warp * 8 * 512 + lane * 16;
 #pragma unroll
@@ -325,24 +355,40 @@ inline bool ring_enabled() {
   return on;
 }
 
+// SB_SEGREDUCE_LANE=0 keeps the row-per-warp arithmetic inside the ring kernel (A/B measurements)
+inline bool lane_enabled() {
+  static const bool on = !(getenv("SB_SEGREDUCE_LANE") && getenv("SB_SEGREDUCE_LANE")[0] == '0');
+  return on;
+}
+
+template <typename A, int SHAPE, bool LANE>
+bool launch_ring(sb_ctx* ctx, A* buf, size_t n, size_t tiles) {
+  constexpr size_t smem = (size_t)SRR_STAGES * SRR_TILE_BYTES;
+  static bool configured[64] = {};
+  if(ctx->device < 0 || ctx->device >= 64) return false;
+  if(!configured[ctx->device]) {
+    if(cudaFuncSetAttribute(segreduce_ring_kernel<A, SHAPE, LANE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) configured[ctx->device] = true;
+    (void)cudaGetLastError();
+    if(!configured[ctx->device]) return false;
+  }
+  size_t grid = (size_t)ctx->sm_count;
+  if(grid > tiles) grid = tiles;
+  // every CTA's producer draws tickets until one is past the last tile: tiles + grid tickets per launch
+  const unsigned long long tbase = ctx->scan_ticket_base;
+  segreduce_ring_kernel<A, SHAPE, LANE><<<(unsigned)grid, (SRR_NW + 1) * 32, smem, ctx->stream>>>(buf, n, (long long)tiles, ctx->scan_ticket, tbase);
+  if(cudaPeekAtLastError() == cudaSuccess) ctx->scan_ticket_base += tiles + grid;
+  return true;
+}
+
 template <typename A, int SHAPE>
 void launch_rows(sb_ctx* ctx, A* buf, size_t n, size_t blocks) {
   constexpr size_t TILE = SRR_TILE_BYTES / sizeof(A);
   const size_t tiles = (n + TILE - 1) / TILE;
   if(ring_enabled() && tiles >= 4) {
-    constexpr size_t smem = (size_t)SRR_STAGES * SRR_TILE_BYTES;
-    static bool configured[64] = {};
-    if(ctx->device >= 0 && ctx->device < 64 && !configured[ctx->device]) {
-      if(cudaFuncSetAttribute(segreduce_ring_kernel<A, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) configured[ctx->device] = true;
-      (void)cudaGetLastError();
-    }
-    if(ctx->device >= 0 && ctx->device < 64 && configured[ctx->device]) {
-      size_t grid = (size_t)ctx->sm_count;
-      if(grid > tiles) grid = tiles;
-      // every CTA's producer draws tickets until one is past the last tile: tiles + grid tickets per launch
-      const unsigned long long tbase = ctx->scan_ticket_base;
-      segreduce_ring_kernel<A, SHAPE><<<(unsigned)grid, (SRR_NW + 1) * 32, smem, ctx->stream>>>(buf, n, (long long)tiles, ctx->scan_ticket, tbase);
-      if(cudaPeekAtLastError() == cudaSuccess) ctx->scan_ticket_base += tiles + grid;
+    constexpr bool CAN_LANE = SHAPE == 8 || SHAPE == 16 || SHAPE == 32;
+    if(CAN_LANE && lane_enabled()) {
+      if(launch_ring<A, SHAPE, CAN_LANE>(ctx, buf, n, tiles)) return;
+    } else if(launch_ring<A, SHAPE, false>(ctx, buf, n, tiles)) {
       return;
     }
   }

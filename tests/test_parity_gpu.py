@@ -231,6 +231,37 @@ def test_segscan_explicit_flags(ctx, O, t, density, exclusive):
     assert_close(t, y2[1:].cpu().numpy(), O.scan(t, hx[1:], exclusive, 0, flags[1:]), n, "flags unaligned")
 
 
+@pytest.mark.parametrize("t", ALL4)
+@pytest.mark.parametrize("case", ["every256", "every256_one_tile_open", "every3", "random"])
+@pytest.mark.parametrize("exclusive", [False, True])
+def test_segscan_explicit_flags_gated_pair(ctx, O, t, case, exclusive):
+    """From 64 tiles on, explicit flags launch a check kernel and BOTH persistent kernels, gated by the check's verdict
+    (csrc/sb_scan.cu: flags_tile_heads_kernel): the independent-tile kernel when every tile starts on a head, the
+    look-back kernel otherwise.  Both verdicts, repeated launches on one ctx (the gated-off kernel must leave the
+    tile ticket where the host mirror expects it), a ragged last tile."""
+    n = (1 << 20) + 777
+    flags = np.zeros(n, dtype=np.uint8)
+    if case.startswith("every256"):
+        flags[::256] = 1
+        if case.endswith("open"):
+            # clear every head that could be the first element of a tile of any instantiation (tiles are multiples of 512)
+            flags[5376 * 8 :: 5376 * 8] = 0
+            flags[12288 * 3] = 0
+    elif case == "every3":
+        flags[::3] = 1
+    else:
+        flags[np.random.default_rng(5).random(n) < 1e-4] = 1
+    hx = rand_input(t, n)
+    x, f = dev(hx), dev(flags)
+    for rep in range(3):
+        y = torch.zeros_like(x)
+        ctx.segscan(x, y, head_flags=f, exclusive=exclusive)
+        assert_close(t, y.cpu().numpy(), O.scan(t, hx, exclusive, 0, flags), n, f"flags {case} rep {rep}")
+        # a ticketed kernel in between: group-scope scan (independent tiles, draws tile tickets)
+        ctx.scan(x, y, exclusive=exclusive, group_len=256)
+        assert_close(t, y.cpu().numpy(), O.scan(t, hx, exclusive, 256), n, f"group scan after flags {case} rep {rep}")
+
+
 # ---------------------------------------------------------------------------------------- segreduce
 @pytest.mark.parametrize("t", ["i16", "i32", "i64", "f32", "f64"])
 @pytest.mark.parametrize("L", [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 16384, 6, 100, 1000])
