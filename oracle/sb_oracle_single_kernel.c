@@ -119,3 +119,81 @@ DEFINE_SCALAR_PROD(f64, double, double)
 
 DEFINE_LINREG(f32, float)
 DEFINE_LINREG(f64, double)
+
+/* ---- single-kernel/lin_reg_error.cpp and single-kernel/kmeans.cpp (the rows the path widens into next) -------------
+ *
+ * Parity status of ref_lin_reg_error_*: PINNED WITHIN TOLERANCE, not bit for bit.  The reference is built with
+ * -O3 -ffast-math (CMakeLists.txt:17), which lets the compiler reassociate and vectorise the inner sum
+ * `error += e * e` (lin_reg_error.cpp:71-74): the order of its additions is whatever gcc chose, not something a
+ * restatement can follow.  What is pinned (tests/test_single_kernel_widened.py against
+ * tests/golden/single_kernel_widened_golden.json, made from oracle/_ref/lin_reg_error): the inputs, regenerated with
+ * the reference's own rand() sequence (:38-43), bit for bit where the golden file records them, and every output
+ * element within the north-star tolerance plus the reference's own criterion (relative L2 error < 1e-6, :80-103).
+ * ref_kmeans_*: PINNED bit for bit (integer output) to oracle/_ref/kmeans.
+ */
+#include <float.h>
+
+#define DEFINE_LINREG_ERROR(SUF, T)                                                                                     \
+  /* LinearRegressionBench::setup, lin_reg_error.cpp:30-43: four rand() draws per element, in1, in2, alpha, beta.    \
+   * `skip` draws are discarded first: the binary runs <float> and then <double> on one rand() stream (:129-133),    \
+   * so the fp64 inputs of --size=N start 4*N draws in. */                                                            \
+  ORACLE_API void ref_lin_reg_error_inputs_##SUF(size_t n, size_t skip, T* in1, T* in2, T* alpha, T* beta) {            \
+    srand(1); /* the C default seed: the reference never calls srand */                                                \
+    for(size_t i = 0; i < skip; ++i) (void)rand();                                                                      \
+    for(size_t i = 0; i < n; ++i) {                                                                                     \
+      in1[i] = (T)rand() / (T)RAND_MAX;                                                                                 \
+      in2[i] = (T)rand() / (T)RAND_MAX;                                                                                 \
+      alpha[i] = (T)rand() / (T)RAND_MAX;                                                                               \
+      beta[i] = (T)rand() / (T)RAND_MAX;                                                                                \
+    }                                                                                                                   \
+  }                                                                                                                     \
+  /* the kernel, lin_reg_error.cpp:64-77: out[g] = sum_i ((alpha[g] * in1[i] + beta[g]) - in2[i])^2, added in index  \
+   * order in T (volatile: one rounding per operation, no contraction). */                                            \
+  ORACLE_API void ref_lin_reg_error_##SUF(const T* in1, const T* in2, const T* alpha, const T* beta, size_t n, T* out) { \
+    _Pragma("omp parallel for schedule(static)")                                                                        \
+    for(size_t g = 0; g < n; ++g) {                                                                                     \
+      const T a = alpha[g], b = beta[g];                                                                                \
+      T error = 0;                                                                                                      \
+      for(size_t i = 0; i < n; ++i) {                                                                                   \
+        volatile T ax = a * in1[i];                                                                                     \
+        volatile T axb = ax + b;                                                                                        \
+        volatile T e = axb - in2[i];                                                                                    \
+        volatile T ee = e * e;                                                                                          \
+        error += ee;                                                                                                    \
+      }                                                                                                                 \
+      out[g] = error;                                                                                                   \
+    }                                                                                                                   \
+  }
+
+DEFINE_LINREG_ERROR(f32, float)
+DEFINE_LINREG_ERROR(f64, double)
+
+#define DEFINE_KMEANS(SUF, T)                                                                                           \
+  /* the kernel, kmeans.cpp:61-79.  features: nfeatures x n (feature-major, :70), clusters: read at [i*nfeatures+l]  \
+   * (:70; the buffer upstream allocates is 3*n long, only nclusters*nfeatures elements are read).  The reference    \
+   * stores the point's own index, not the cluster's (`index = gid`, :74): membership[g] = g as soon as any distance  \
+   * is below the running minimum, which starts at FLT_MAX (<cfloat>'s, reached through the SYCL headers; the #ifndef \
+   * fallback of :4-6 is dead).  A NaN distance compares false. */                                                    \
+  ORACLE_API void ref_kmeans_##SUF(const T* features, const T* clusters, size_t n, int nfeatures, int nclusters,        \
+      int* membership) {                                                                                                \
+    for(size_t g = 0; g < n; ++g) {                                                                                     \
+      int index = 0;                                                                                                    \
+      T min_dist = (T)FLT_MAX;                                                                                          \
+      for(int i = 0; i < nclusters; ++i) {                                                                              \
+        T dist = 0;                                                                                                     \
+        for(int l = 0; l < nfeatures; ++l) {                                                                            \
+          volatile T d = features[(size_t)l * n + g] - clusters[i * nfeatures + l];                                     \
+          volatile T dd = d * d;                                                                                        \
+          dist += dd;                                                                                                   \
+        }                                                                                                               \
+        if(dist < min_dist) {                                                                                           \
+          min_dist = dist;                                                                                              \
+          index = (int)g;                                                                                               \
+        }                                                                                                               \
+      }                                                                                                                 \
+      membership[g] = index;                                                                                            \
+    }                                                                                                                   \
+  }
+
+DEFINE_KMEANS(f32, float)
+DEFINE_KMEANS(f64, double)

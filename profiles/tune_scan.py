@@ -44,6 +44,9 @@ def worker(args):
             "scan_cyclic": (lambda: ctx.scan_cyclic(x, y), 2 * n * size[t]),
             "scan_group256": (lambda: ctx.scan(x, y, exclusive=True, group_len=256), 2 * n * size[t]),
             "segscan_L65536": (lambda: ctx.segscan(x, y, seg_len=65536), 2 * n * size[t]),
+            "segscan_L16384": (lambda: ctx.segscan(x, y, seg_len=16384), 2 * n * size[t]),
+            "segscan_L1M": (lambda: ctx.segscan(x, y, seg_len=1 << 20), 2 * n * size[t]),
+            "segscan_L50000": (lambda: ctx.segscan(x, y, seg_len=50000), 2 * n * size[t]),
             "segreduce256": (lambda: ctx.segreduce(y, 256), n * size[t] + n // 256 * size[t]),
             "segreduce64": (lambda: ctx.segreduce(y, 64), n * size[t] + n // 64 * size[t]),
             "segreduce128": (lambda: ctx.segreduce(y, 128), n * size[t] + n // 128 * size[t]),

@@ -35,6 +35,7 @@ struct sb_ctx {
   unsigned long long* scan_ticket = nullptr;  // monotonically increasing, never reset
   unsigned long long scan_ticket_base = 0;    // host mirror of the value the next launch starts at
   uint32_t scan_epoch = 0;                    // descriptor generation, bumped per launch
+  unsigned long long flags_gate_seq = 0;      // explicit-flag scans: number of the last tile-head check (sb_scan.cu)
 
   // sb_scan_cyclic on one GPU: a private peer group of world size 1 (created on first use)
   sb_peer* self_peer = nullptr;

@@ -108,6 +108,9 @@ constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
 #define SB_WS_NW_LB64 14  // 64-bit types, segmented modes with look-back: 14 + 2 = 16 warps -> 128 registers per thread
 #endif
 constexpr int WS_NW_LB64 = SB_WS_NW_LB64;
+#ifndef SB_SCAN_SEG_EARLY
+#define SB_SCAN_SEG_EARLY 1  // explicit flags, 32-bit: the look-back waits only for the descriptors up to the nearest head
+#endif
 constexpr int WS_NSLOT = 2 * WS_DEPTH + 2;  // a fast warp is at most DEPTH+1 tiles ahead of a slow one
 
 using namespace sbscan;
@@ -186,14 +189,41 @@ __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, 
     // Poll until every descriptor of the window is there, re-issuing ALL missing loads of a pass back to back: one
     // L2 round trip per pass.  (Waiting for them one after the other cost up to U + 1 dependent round trips of
     // ~1.1 us each under load — the phase trace showed look-backs of 4-8 us after the last aggregate was out.)
+    // Explicit flags, 32-bit types (SB_SCAN_SEG_EARLY): the walk ends at the NEAREST predecessor that holds a head, so only
+    // the descriptors from there to this tile are waited for — with heads in (almost) every tile a tile depends on one
+    // neighbour instead of on every tile in front of it in the round.  Measured at 2^28 with heads at random positions,
+    // mean distance 256 (profiles/r02_ops_v12_seg_early_ab.jsonl): int32 4.20 -> 4.36, fp32 3.85 -> 4.15 TB/s; but 64-bit
+    // types LOSE 8-11 % (3.11 -> 2.85) and implicit heads (L = 65536 ... 2^20) 0-6 %: those kernels are bound by their
+    // instruction count, not by the descriptor chain, and the two extra ballots per window sit in the look-back warp's
+    // critical path.  Hence only where it measured faster.
     for(;;) {
       bool missing = false;
+      if(MODE == MODE_FLAGS && sizeof(A) == 4 && SB_SCAN_SEG_EARLY) {
+        int stop_u = U;  // window of the nearest head seen so far (warp-uniform)
 #pragma unroll
-      for(int u = 0; u < U; ++u) {
-        const int q = hi - 1 - (u * 32 + lane);
-        if(q >= 0 && (st[u] >> 2) != epoch) {
-          missing = true;
-          Desc<A>::load(row + q, st[u], val[u]);
+        for(int u = 0; u < U; ++u) {
+          if(u > stop_u) continue;
+          const int q = hi - 1 - (u * 32 + lane);
+          const bool present = q < 0 || (st[u] >> 2) == epoch;
+          const unsigned heads = __ballot_sync(SB_FULL_MASK, q >= 0 && present && (st[u] & 3u) == ST_INCL);
+          unsigned need = 0xffffffffu;  // lanes of this window whose descriptors the walk needs (lane 0 = nearest)
+          if(heads) {
+            need = 0xffffffffu >> (32 - __ffs(heads));
+            stop_u = u;
+          }
+          if(!present && ((need >> lane) & 1u)) {
+            missing = true;
+            Desc<A>::load(row + q, st[u], val[u]);
+          }
+        }
+      } else {
+#pragma unroll
+        for(int u = 0; u < U; ++u) {
+          const int q = hi - 1 - (u * 32 + lane);
+          if(q >= 0 && (st[u] >> 2) != epoch) {
+            missing = true;
+            Desc<A>::load(row + q, st[u], val[u]);
+          }
         }
       }
       if(lane == 0 && r > 0 && (rst >> 2) != epoch) Desc<A>::load(rdesc + (r - 1), rst, rval);  // keep the round prefix polling too
@@ -208,7 +238,8 @@ __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, 
     for(int u = 0; u < U; ++u) {
       if(head_found) break;
       if(MODE != MODE_PLAIN) {
-        const unsigned heads = __ballot_sync(SB_FULL_MASK, (st[u] & 3u) == ST_INCL);
+        // (the epoch test matters with SB_SCAN_SEG_EARLY: descriptors behind the nearest head may still be stale)
+        const unsigned heads = __ballot_sync(SB_FULL_MASK, (st[u] >> 2) == epoch && (st[u] & 3u) == ST_INCL);
         if(heads) {
           const int first = __ffs(heads) - 1;  // lowest lane = nearest predecessor with a head
           if(lane <= first) lane_sum += val[u];
@@ -318,13 +349,13 @@ template <typename A, int MODE, int K, int NW>
 __global__ void __launch_bounds__((NW + 2) * 32, SB_WS_MINB)
 scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
     const A* __restrict__ seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, long long num_tiles, int flags_in_ring,
-    unsigned* err, unsigned long long timeout_ns, const unsigned* gate, unsigned gate_want) {
+    unsigned* err, unsigned long long timeout_ns, const unsigned long long* gate, unsigned long long gate_seq, int gate_want) {
   using C = TileCfg<A, NW, K>;
   constexpr int VEC = C::VEC;
   constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K, NW>();
   extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x STAGE_BYTES
   __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES], agg_bar[WS_NSLOT], prefix_bar[WS_NSLOT];
-  if(gate && *gate != gate_want) return;  // explicit flags: the other kernel of the pair runs (flags_tile_heads_kernel)
+  if(gate && (int)(*gate == gate_seq) != gate_want) return;  // explicit flags: the other kernel of the pair runs (flags_tile_heads_kernel)
   __shared__ A s_wagg[WS_NSLOT][NW];
   __shared__ int s_wflag[WS_NSLOT][NW];
   __shared__ A s_tprefix[WS_NSLOT];
@@ -600,14 +631,14 @@ constexpr int WS_TILE_IDS = 8;  // ring of tile ids handed from the producer to 
 template <typename A, int MODE, int K, int NW>
 __global__ void __launch_bounds__((NW + 1) * 32, SB_WS_MINB)
 scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
-    long long num_tiles, int flags_in_ring, unsigned long long* ticket, unsigned long long ticket_base, const unsigned* gate,
-    unsigned gate_want) {
+    long long num_tiles, int flags_in_ring, unsigned long long* ticket, unsigned long long ticket_base, const unsigned long long* gate,
+    unsigned long long gate_seq, int gate_want) {
   using C = TileCfg<A, NW, K>;
   constexpr int VEC = C::VEC;
   constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K, NW>();
   extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x STAGE_BYTES
   __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES], agg_bar[WS_NSLOT];
-  if(gate && *gate != gate_want) {
+  if(gate && (int)(*gate == gate_seq) != gate_want) {
     // not this kernel's case.  The host has already counted this launch's tickets (tiles + grid): draw them
     if(threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(ticket, (unsigned long long)num_tiles + gridDim.x);
     return;
@@ -695,15 +726,16 @@ scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg
 
 // ---- explicit head flags: does every tile start on a head? ----------------------------------------------------------
 // If so (the benchmark's own flags: a head every `--local` elements, and the tile is a multiple of that) no tile needs
-// anything from another tile and the independent-tile kernel does the job without descriptors, look-back warp and phase A.
-// The host cannot know without a round trip, so it launches this check (one byte per tile: ~3 us for 2^28 elements), then
-// BOTH scan kernels, each of which leaves at once unless the verdict in `gate` names it.
-__global__ void __launch_bounds__(1024) flags_tile_heads_kernel(const uint8_t* __restrict__ flags, long long num_tiles, size_t tile,
-    unsigned* gate) {
-  int ok = 1;
-  for(long long t = 1 + (long long)threadIdx.x; t < num_tiles; t += blockDim.x) ok &= __ldg(flags + (size_t)t * tile) != 0 ? 1 : 0;
-  ok = __syncthreads_and(ok);
-  if(threadIdx.x == 0) *gate = ok ? 1u : 0u;
+// anything from another tile and the independent-tile kernel does the job without descriptors, look-back warp and phase A
+// (2^28 elements: int32 5.04 -> 6.37, fp32 5.24 -> 6.40, int64 4.08 -> 5.03, fp64 4.24 -> 5.65 TB/s).
+// The host cannot know without a round trip, so it launches this check (one byte per tile), then BOTH scan kernels, each
+// of which leaves at once unless the verdict names it.  Verdict: *gate == seq  <=>  some tile of check number `seq` does NOT
+// start on a head (sequence numbers only grow, so atomicMax never needs a reset).
+__global__ void __launch_bounds__(256) flags_tile_heads_kernel(const uint8_t* __restrict__ flags, long long num_tiles, size_t tile,
+    unsigned long long* gate, unsigned long long seq) {
+  const long long t = 1 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int bad = t < num_tiles && __ldg(flags + (size_t)t * tile) == 0 ? 1 : 0;
+  if(__syncthreads_or(bad) && threadIdx.x == 0) atomicMax(gate, seq);
 }
 
 // co-resident CTAs per SM of a persistent kernel instantiation.  The shared-memory opt-in is a per-device
@@ -731,8 +763,8 @@ template <int MODE> struct ws_rows { static constexpr int K = MODE == MODE_FLAGS
 
 template <typename A, int MODE, int NW>
 int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* flags,
-    const A* seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, size_t tiles, const unsigned* gate = nullptr,
-    unsigned gate_want = 0) {
+    const A* seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, size_t tiles, const unsigned long long* gate = nullptr,
+    unsigned long long gate_seq = 0, int gate_want = 0) {
   constexpr int K = ws_rows<MODE>::K;
   constexpr size_t smem = (size_t)WS_STAGES * ws_stage_bytes<A, MODE, K, NW>();
   constexpr int WS_THREADS = (NW + 2) * 32;
@@ -752,7 +784,7 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
     // (the host mirror of the ticket advances only once the launch is known to have been accepted)
     const unsigned long long tbase = ctx->scan_ticket_base;
     scan_independent_kernel<A, MODE, K, NW><<<(unsigned)g, (NW + 1) * 32, smem, ctx->stream>>>(in, out, n, exclusive, seg_len, seg_mask, flags,
-        num_tiles, flags_in_ring, ctx->scan_ticket, tbase, gate, gate_want);
+        num_tiles, flags_in_ring, ctx->scan_ticket, tbase, gate, gate_seq, gate_want);
     if(cudaError_t e = cudaGetLastError(); e != cudaSuccess) return (int)e;
     ctx->scan_ticket_base += tiles + g;
     return SB_OK;
@@ -763,7 +795,7 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
   unsigned long long timeout_ns = sb_peer_timeout_ns();
   void* args[] = {(void*)&in, (void*)&out, (void*)&n, (void*)&exclusive, (void*)&seg_len, (void*)&seg_mask, (void*)&flags, (void*)&seed,
       (void*)&desc, (void*)&epoch, (void*)&use_lookback, (void*)&num_tiles, (void*)&flags_in_ring, (void*)&err, (void*)&timeout_ns,
-      (void*)&gate, (void*)&gate_want};
+      (void*)&gate, (void*)&gate_seq, (void*)&gate_want};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_ws_kernel<A, MODE, K, NW>, dim3((unsigned)grid), dim3(WS_THREADS), args, smem, ctx->stream);
   if(e != cudaSuccess) return (int)e;
   return SB_OK;
@@ -792,7 +824,11 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   // thread may use 128 registers (at 18 warps ptxas has 96 and spills 100-270 bytes, profiles/r02_ptxas_spills.txt).
   // SB_SCAN_LB64_NW=16 keeps the 16-worker instantiation (A/B measurements).
   static const bool lb64_enabled = !(getenv("SB_SCAN_LB64_NW") && atoi(getenv("SB_SCAN_LB64_NW")) == 16);
-  const bool lb64 = lb64_enabled && sizeof(A) == 8 && (mode == MODE_FLAGS || (mode == MODE_IMPLICIT && !narrow));
+  // 64-bit segments of 1024 ... 8192 elements: neither 15 x 8 rows (7680 elements) nor 14 x 8 (7168) is a multiple of them, but
+  // 16 x 8 rows (8192) is — independent tiles with 16 workers (96 registers, a few spills) still beat the look-back kernel
+  // by a wide margin (L = 16384 on the look-back path measured 3.0 TB/s against 5.5-6.6 for independent tiles)
+  const bool mid = mode == MODE_IMPLICIT && sizeof(A) == 8 && !narrow && sb::is_pow2(seg_len) && TileCfg<A, WS_NW, WS_K>::TILE % seg_len == 0;
+  const bool lb64 = lb64_enabled && sizeof(A) == 8 && (mode == MODE_FLAGS || (mode == MODE_IMPLICIT && !narrow && !mid));
   const size_t ws_tile = mode == MODE_FLAGS ? (lb64 ? TileCfg<A, WS_NW_LB64, ws_rows<MODE_FLAGS>::K>::TILE : TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS>::K>::TILE)
                          : wide ? wide_tile : narrow ? narrow_tile : lb64 ? TileCfg<A, WS_NW_LB64, WS_K>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
   const size_t simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
@@ -839,18 +875,21 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
       // explicit flags: check kernel + both scan kernels, gated by its verdict (see flags_tile_heads_kernel).
       // SB_SCAN_FLAGS_GATE=0 launches the look-back kernel alone (A/B measurements).
       static const bool gate_enabled = !(getenv("SB_SCAN_FLAGS_GATE") && getenv("SB_SCAN_FLAGS_GATE")[0] == '0');
-      const unsigned* gate = nullptr;
+      const unsigned long long* gate = nullptr;
+      unsigned long long seq = 0;
       rc = SB_OK;
       if(gate_enabled && use_lookback && tiles >= 64) {
-        unsigned* g = reinterpret_cast<unsigned*>(ctx->scan_ticket + 16);  // byte 128 of the ctx's 256-byte ticket block
-        flags_tile_heads_kernel<<<1, 1024, 0, ctx->stream>>>(flags, (long long)tiles, tile, g);
+        unsigned long long* g = ctx->scan_ticket + 16;  // byte 128 of the ctx's 256-byte ticket block (zeroed at creation)
+        seq = ++ctx->flags_gate_seq;
+        flags_tile_heads_kernel<<<(unsigned)((tiles + 254) / 256), 256, 0, ctx->stream>>>(flags, (long long)tiles, tile, g, seq);
         gate = g;
-        if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, 1u);
-        else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, 1u);
+        // (64-bit types keep the 14-worker tile here too: 15 workers x 6 rows x 64 elements is not a multiple of 256)
+        if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, seq, 0);
+        else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, seq, 0);
       }
       if(rc == SB_OK) {
-        if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles, gate, 0u);
-        else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles, gate, 0u);
+        if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles, gate, seq, 1);
+        else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles, gate, seq, 1);
       }
     }
     if(rc != SB_OK) return rc;
