@@ -167,6 +167,23 @@ int sb_dot_f64(sb_ctx*, const double* a, const double* b, size_t n, double* out)
  * (the reference reduces them in place).  n == 0: the sums are 0 and the coefficients NaN. */
 int sb_linreg_f32(sb_ctx*, const float* x, const float* y, size_t n, float* out6);
 int sb_linreg_f64(sb_ctx*, const double* x, const double* y, size_t n, double* out6);
+/* Squared error of N candidate regression lines over N points:
+ *   out[g] = sum_i ((alpha[g] * x[i] + beta[g]) - y[i])^2,   g < n.
+ * Replaces LinearRegressionBench::run (single-kernel/lin_reg_error.cpp:54-79; in1 = x, in2 = y): one work-item per
+ * candidate, each looping over all N points (N^2 multiply-adds).  Here: one fused streaming reduction of the five sums the
+ * quadratic form needs (x and y read once, double accumulators) and one map over alpha / beta — 5*N*s bytes, two launches.
+ * The result is the correctly rounded value to within a few ulp of double; the reference's sequential sum in T differs
+ * from it by its own rounding error, inside the tolerance the tests state (1e-5*log2 N fp32, 1e-12*log2 N fp64).
+ * Conditioning: a candidate that fits the points almost exactly has an error far below the O(N) sums it is computed
+ * from; such values are accurate to a few N * 2^-52 in absolute terms (fp64, N = 2^22: 1e-10), not relatively. */
+int sb_linreg_error_f32(sb_ctx*, const float* x, const float* y, const float* alpha, const float* beta, size_t n, float* out);
+int sb_linreg_error_f64(sb_ctx*, const double* x, const double* y, const double* alpha, const double* beta, size_t n, double* out);
+/* Nearest-cluster pass of k-means as the reference computes it (single-kernel/kmeans.cpp:49-82): features are stored
+ * feature-major (features[l*n + g]), clusters[k*nfeatures + l]; distances are summed in T.  The reference records the
+ * POINT's index, not the cluster's (`index = gid`, :74): membership[g] = (int)g if some cluster's squared distance is below
+ * the running minimum — which starts at FLT_MAX (:66) —, else 0.  Bit-exact. */
+int sb_kmeans_f32(sb_ctx*, const float* features, const float* clusters, size_t n, int nfeatures, int nclusters, int32_t* membership);
+int sb_kmeans_f64(sb_ctx*, const double* features, const double* clusters, size_t n, int nfeatures, int nclusters, int32_t* membership);
 
 /* ---- segmented reduction -------------------------------------------------------------------- */
 /* In place, reference layout (pattern/segmentedreduction.cpp:35-61,63-96; contract :112-119):

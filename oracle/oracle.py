@@ -69,6 +69,13 @@ def lib() -> C.CDLL:
             getattr(L, f"ref_scalar_prod_{t}").argtypes = [vp, vp, sz, sz, vp]
         for t in ("f32", "f64"):
             getattr(L, f"ref_linreg_{t}").argtypes = [vp, vp, sz, sz, vp]
+            # single-kernel/lin_reg_error, kmeans
+            getattr(L, f"ref_lin_reg_error_inputs_{t}").argtypes = [sz, sz, vp, vp, vp, vp]
+            getattr(L, f"ref_lin_reg_error_inputs_{t}").restype = None
+            getattr(L, f"ref_lin_reg_error_{t}").argtypes = [vp, vp, vp, vp, sz, vp]
+            getattr(L, f"ref_lin_reg_error_{t}").restype = None
+            getattr(L, f"ref_kmeans_{t}").argtypes = [vp, vp, sz, i, i, vp]
+            getattr(L, f"ref_kmeans_{t}").restype = None
         L.kat_reduce.argtypes = [u64]
         L.kat_reduce.restype = u64
         L.kat_scan.argtypes = [u64, i, u64]
@@ -127,6 +134,31 @@ def scalar_prod(t: str, a: np.ndarray, b: np.ndarray, L: int):
     if rc != 0:
         raise ValueError("ref_scalar_prod: n and L must be positive")
     return out[0]
+
+
+def lin_reg_error_inputs(t: str, n: int, skip: int = 0):
+    """single-kernel/lin_reg_error.cpp:30-43 restated: (in1, in2, alpha, beta) from the C rand() stream, default seed,
+    after discarding `skip` draws (the fp64 benchmark of one process starts 4 * size draws in)."""
+    arrs = [np.empty(n, dtype=NP[t]) for _ in range(4)]
+    getattr(lib(), f"ref_lin_reg_error_inputs_{t}")(n, skip, *[a.ctypes.data for a in arrs])
+    return arrs
+
+
+def lin_reg_error(t: str, in1: np.ndarray, in2: np.ndarray, alpha: np.ndarray, beta: np.ndarray) -> np.ndarray:
+    """single-kernel/lin_reg_error.cpp:64-77 restated: out[g] = sum_i ((alpha[g] * in1[i] + beta[g]) - in2[i])^2 in T."""
+    n = in1.size
+    assert in2.size == n and alpha.size == n and beta.size == n
+    out = np.empty(n, dtype=NP[t])
+    getattr(lib(), f"ref_lin_reg_error_{t}")(in1.ctypes.data, in2.ctypes.data, alpha.ctypes.data, beta.ctypes.data, n, out.ctypes.data)
+    return out
+
+
+def kmeans(t: str, features: np.ndarray, clusters: np.ndarray, n: int, nfeatures: int = 2, nclusters: int = 3) -> np.ndarray:
+    """single-kernel/kmeans.cpp:61-79 restated: membership[g] = g if any cluster distance is below FLT_MAX, else 0."""
+    assert features.size >= nfeatures * n and clusters.size >= nclusters * nfeatures
+    out = np.empty(n, dtype=np.int32)
+    getattr(lib(), f"ref_kmeans_{t}")(features.ctypes.data, clusters.ctypes.data, n, nfeatures, nclusters, out.ctypes.data)
+    return out
 
 
 def linreg(t: str, x: np.ndarray, y: np.ndarray, L: int) -> np.ndarray:

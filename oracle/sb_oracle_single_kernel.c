@@ -1,5 +1,6 @@
 /* sb_oracle_single_kernel.c — CPU restatement of single-kernel/scalar_prod.cpp and
- * single-kernel/lin_reg_coeff.cpp of the reference.
+ * single-kernel/lin_reg_coeff.cpp of the reference, and — second half of the file, with its own
+ * parity note — of single-kernel/lin_reg_error.cpp and single-kernel/kmeans.cpp.
  *
  * TEST INFRASTRUCTURE ONLY (same rule as sb_oracle.c): never called, linked or loaded by the product.
  *

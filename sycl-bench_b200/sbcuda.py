@@ -121,6 +121,8 @@ def lib() -> C.CDLL:
         getattr(L, f"sb_dot_{t}").argtypes = [vp, vp, vp, sz, vp]
     for t in ("f32", "f64"):
         getattr(L, f"sb_linreg_{t}").argtypes = [vp, vp, vp, sz, vp]
+        getattr(L, f"sb_linreg_error_{t}").argtypes = [vp, vp, vp, vp, vp, sz, vp]
+        getattr(L, f"sb_kmeans_{t}").argtypes = [vp, vp, vp, sz, i, i, vp]
     L.sb_host_reduce.argtypes = [vp, i, vp, sz, vp]
     L.sb_host_scan.argtypes = [vp, i, vp, vp, sz, i, sz]
     L.sb_host_segreduce.argtypes = [vp, i, vp, sz, sz]
@@ -268,6 +270,19 @@ class Context:
         n = x.numel() if n is None else n
         _check(getattr(lib(), f"sb_linreg_{t}")(self._h, _ptr(x), _ptr(y), n, _ptr(out6)))
         return out6
+
+    def linreg_error(self, x, y, alpha, beta, out, n: Optional[int] = None, dtype: Optional[str] = None):
+        """out[g] = sum_i ((alpha[g] * x[i] + beta[g]) - y[i])^2 (single-kernel/lin_reg_error.cpp:64-77)."""
+        t = dtype or dtype_of(x)
+        n = x.numel() if n is None else n
+        _check(getattr(lib(), f"sb_linreg_error_{t}")(self._h, _ptr(x), _ptr(y), _ptr(alpha), _ptr(beta), n, _ptr(out)))
+        return out
+
+    def kmeans(self, features, clusters, membership, n: int, nfeatures: int = 2, nclusters: int = 3, dtype: Optional[str] = None):
+        """membership[g] = g if any cluster distance < FLT_MAX else 0 (single-kernel/kmeans.cpp:61-79)."""
+        t = dtype or dtype_of(features)
+        _check(getattr(lib(), f"sb_kmeans_{t}")(self._h, _ptr(features), _ptr(clusters), n, nfeatures, nclusters, _ptr(membership)))
+        return membership
 
     def scan(self, x, out, exclusive: bool = False, group_len: int = 0, seed=None, n: Optional[int] = None, dtype: Optional[str] = None):
         t = dtype or dtype_of(x)

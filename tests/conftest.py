@@ -20,7 +20,7 @@ def _native_artefacts_built():
     needed = [os.path.join(ROOT, "sycl-bench_b200", "lib", "libsb_cuda.so"), os.path.join(ROOT, "oracle", "_build", "liboracle.so")]
     needed += [os.path.join(ROOT, "sycl-bench_b200", "bin", b) for b in (
         "reduction", "prefixsum", "scan", "segmentedreduction", "segmentedscan", "atomic_reduction", "reduce_over_group",
-        "kernel_reduction", "scalar_prod", "lin_reg_coeff", "DRAM")]
+        "kernel_reduction", "scalar_prod", "lin_reg_coeff", "lin_reg_error", "kmeans", "DRAM")]
     if not all(os.path.exists(p) for p in needed):
         import __graft_entry__ as ge
 

@@ -129,7 +129,7 @@ def test_run_suite_quicktest(tmp_path):
     from oracle import oracle as O
 
     table = O.parse_csv(str(out))
-    assert len(table) == 4 + 4 + 8 + 5 + 8 + 4 + 4 + 12 + 4 + 2 + 6  # pattern/ + sycl2020/ trio + single-kernel/ + micro/DRAM rows
+    assert len(table) == 4 + 4 + 8 + 5 + 8 + 4 + 4 + 12 + 4 + 2 + 2 + 2 + 6  # pattern/ + sycl2020/ trio + single-kernel/ + micro/DRAM rows
     assert all(row["Verification"] == "PASS" for row in table.values())
     r = subprocess.run([os.path.join(ROOT, "sycl-bench_b200", "run-suite"), "quicktest", f"--output={out}"], capture_output=True, text=True)
     assert r.returncode == 1 and "already exists" in r.stdout
