@@ -309,107 +309,118 @@ int linreg_error_impl(sb_ctx* ctx, const T* x, const T* y, const T* alpha, const
 // 2 x 128-bit stores), the cluster table sits in shared memory.  Distances are summed in T in the reference's order with
 // one rounding per operation.
 constexpr int KM_MAX_TABLE = 2048;  // cluster-table elements kept in shared memory
-constexpr int KM_NF_REG = 4;        // features per point held in registers over the cluster loop
 
-template <typename A, bool VECTOR>
+// NFR > 0: the point's features (nfeatures <= NFR) are read once and stay in registers over the cluster loop, U vectors of
+// points per thread (all U * nfeatures 128-bit loads of a thread are issued before the first use: with one vector per thread
+// the kernel had 32 bytes in flight per thread and ran at 4.0-4.4 TB/s of DRAM traffic).  NFR == 0: any nfeatures, the rows
+// are re-read per cluster (they stay in L1 / L2).
+template <typename A, bool VECTOR, int NFR, int U>
 __global__ void __launch_bounds__(256) kmeans_kernel(const A* __restrict__ features, const A* __restrict__ clusters, size_t n, int nfeatures,
     int nclusters, int* __restrict__ membership) {
   constexpr int VEC = VECTOR ? 16 / sizeof(A) : 1;
+  constexpr int NF = NFR > 0 ? NFR : 1;
   __shared__ A table[KM_MAX_TABLE];
   const int tsize = nfeatures * nclusters;
   const bool in_smem = tsize <= KM_MAX_TABLE;
   const A* tab = in_smem ? table : clusters;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t g0 = i * VEC;
-  const int cnt = g0 >= n ? 0 : (n - g0 < (size_t)VEC) ? (int)(n - g0) : VEC;
-  // (the cluster table is staged AFTER the point's feature loads have been issued, see below: staging it first put two
-  // dependent memory latencies into the life of every 256-thread block — fp64 2^28 points ran at 3.1 TB/s)
-  auto stage_table = [&] {
-    if(in_smem) {
-      for(int k = threadIdx.x; k < tsize; k += blockDim.x) table[k] = clusters[k];
-      __syncthreads();
-    }
-  };
-  A min_dist[VEC];
-  int index[VEC];
+  const size_t v0 = (size_t)blockIdx.x * (256 * U) + threadIdx.x;  // the thread's vectors: v0 + u * 256
+  A f[U][NF][VEC];
+  int cnt[U];
 #pragma unroll
-  for(int c = 0; c < VEC; ++c) {
-    min_dist[c] = (A)3.402823466e+38f;  // FLT_MAX, kmeans.cpp:66
-    index[c] = 0;
+  for(int u = 0; u < U; ++u) {
+    const size_t g0 = (v0 + (size_t)u * 256) * VEC;
+    cnt[u] = g0 >= n ? 0 : (n - g0 < (size_t)VEC) ? (int)(n - g0) : VEC;
   }
-  auto load_row = [&](int l, A (&f)[VEC]) {
-    const A* row = features + (size_t)l * n + g0;
-    if(VECTOR && cnt == VEC) {
-      const sb::Vec<A> t = sb::ldg_nc<A>(row);
+  if(NFR > 0) {
 #pragma unroll
-      for(int c = 0; c < VEC; ++c) f[c] = t.v[c];
-    } else {
+    for(int u = 0; u < U; ++u) {
+      const size_t g0 = (v0 + (size_t)u * 256) * VEC;
 #pragma unroll
-      for(int c = 0; c < VEC; ++c) f[c] = c < cnt ? __ldg(row + c) : A(0);
-    }
-  };
-  auto take = [&](const A (&dist)[VEC]) {  // kmeans.cpp:72-75
+      for(int l = 0; l < NF; ++l) {
+        if(l < nfeatures) {
+          const A* row = features + (size_t)l * n + g0;
+          if(VECTOR && cnt[u] == VEC) {
+            const sb::Vec<A> t = sb::ldg_nc_ordered<A>(row);
 #pragma unroll
-    for(int c = 0; c < VEC; ++c) {
-      if(dist[c] < min_dist[c]) {
-        min_dist[c] = dist[c];
-        index[c] = (int)(g0 + c);  // the reference narrows the size_t global id to int the same way
+            for(int c = 0; c < VEC; ++c) f[u][l][c] = t.v[c];
+          } else {
+#pragma unroll
+            for(int c = 0; c < VEC; ++c) f[u][l][c] = c < cnt[u] ? __ldg(row + c) : A(0);
+          }
+        }
       }
     }
-  };
-  if(nfeatures <= KM_NF_REG) {
-    // the point's features are read once and stay in registers over the cluster loop
-    A f[KM_NF_REG][VEC];
+  }
+  // the cluster table is staged AFTER the feature loads have been issued (staging it first put two dependent memory
+  // latencies into the life of every block: fp64, 2^28 points 1.72 -> 1.34 ms)
+  if(in_smem) {
+    for(int k = threadIdx.x; k < tsize; k += blockDim.x) table[k] = clusters[k];
+    __syncthreads();
+  }
 #pragma unroll
-    for(int l = 0; l < KM_NF_REG; ++l)
-      if(l < nfeatures) load_row(l, f[l]);
-    stage_table();
+  for(int u = 0; u < U; ++u) {
+    if(cnt[u] == 0) continue;
+    const size_t g0 = (v0 + (size_t)u * 256) * VEC;
+    A min_dist[VEC];
+    int index[VEC];
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) {
+      min_dist[c] = (A)3.402823466e+38f;  // FLT_MAX, kmeans.cpp:66
+      index[c] = 0;
+    }
     for(int k = 0; k < nclusters; ++k) {
       A dist[VEC];
 #pragma unroll
       for(int c = 0; c < VEC; ++c) dist[c] = A(0);
+      if(NFR > 0) {
 #pragma unroll
-      for(int l = 0; l < KM_NF_REG; ++l) {
-        if(l < nfeatures) {
+        for(int l = 0; l < NF; ++l) {
+          if(l < nfeatures) {
+            const A cl = tab[k * nfeatures + l];
+#pragma unroll
+            for(int c = 0; c < VEC; ++c) {
+              const A d = sub_rn<A>(f[u][l][c], cl);
+              dist[c] += mul_rn<A>(d, d);
+            }
+          }
+        }
+      } else {
+        for(int l = 0; l < nfeatures; ++l) {
           const A cl = tab[k * nfeatures + l];
+          const A* row = features + (size_t)l * n + g0;
 #pragma unroll
           for(int c = 0; c < VEC; ++c) {
-            const A d = sub_rn<A>(f[l][c], cl);
+            const A d = sub_rn<A>(c < cnt[u] ? __ldg(row + c) : A(0), cl);
             dist[c] += mul_rn<A>(d, d);
           }
         }
       }
-      take(dist);
-    }
-  } else {
-    // many features: re-read per cluster (the rows of a block stay in L1 / L2)
-    stage_table();
-    for(int k = 0; k < nclusters; ++k) {
-      A dist[VEC];
 #pragma unroll
-      for(int c = 0; c < VEC; ++c) dist[c] = A(0);
-      for(int l = 0; l < nfeatures; ++l) {
-        const A cl = tab[k * nfeatures + l];
-        const A* row = features + (size_t)l * n + g0;
-#pragma unroll
-        for(int c = 0; c < VEC; ++c) {
-          const A d = sub_rn<A>(c < cnt ? __ldg(row + c) : A(0), cl);
-          dist[c] += mul_rn<A>(d, d);
+      for(int c = 0; c < VEC; ++c) {  // kmeans.cpp:72-75
+        if(dist[c] < min_dist[c]) {
+          min_dist[c] = dist[c];
+          index[c] = (int)(g0 + c);  // the reference narrows the size_t global id to int the same way
         }
       }
-      take(dist);
+    }
+    if(VECTOR && cnt[u] == VEC && (reinterpret_cast<uintptr_t>(membership + g0) & (4 * VEC - 1)) == 0) {
+      if constexpr(VEC == 4) *reinterpret_cast<int4*>(membership + g0) = make_int4(index[0], index[1], index[2], index[3]);
+      else if constexpr(VEC == 2) *reinterpret_cast<int2*>(membership + g0) = make_int2(index[0], index[1]);
+      else membership[g0] = index[0];
+    } else {
+#pragma unroll
+      for(int c = 0; c < VEC; ++c)
+        if(c < cnt[u]) membership[g0 + c] = index[c];
     }
   }
-  if(cnt == 0) return;
-  if(VECTOR && cnt == VEC && (reinterpret_cast<uintptr_t>(membership + g0) & (4 * VEC - 1)) == 0) {
-    if constexpr(VEC == 4) *reinterpret_cast<int4*>(membership + g0) = make_int4(index[0], index[1], index[2], index[3]);
-    else if constexpr(VEC == 2) *reinterpret_cast<int2*>(membership + g0) = make_int2(index[0], index[1]);
-    else membership[g0] = index[0];
-  } else {
-#pragma unroll
-    for(int c = 0; c < VEC; ++c)
-      if(c < cnt) membership[g0 + c] = index[c];
-  }
+}
+
+template <typename T, bool VECTOR, int NFR, int U>
+void kmeans_launch(sb_ctx* ctx, const T* features, const T* clusters, size_t n, int nfeatures, int nclusters, int32_t* membership) {
+  const size_t vec = VECTOR ? 16 / sizeof(T) : 1;
+  const size_t per_block = 256 * (size_t)U * vec;
+  const size_t blocks = (n + per_block - 1) / per_block;
+  kmeans_kernel<T, VECTOR, NFR, U><<<(unsigned)blocks, 256, 0, ctx->stream>>>(features, clusters, n, nfeatures, nclusters, membership);
 }
 
 template <typename T>
@@ -417,14 +428,18 @@ int kmeans_impl(sb_ctx* ctx, const T* features, const T* clusters, size_t n, int
   if(!ctx || nfeatures < 0 || nclusters < 0 || (n && (!membership || (nfeatures && !features) || (nfeatures && nclusters && !clusters)))) return SB_ERR_BAD_ARG;
   if(!sb::aligned_to(features, sizeof(T)) || !sb::aligned_to(clusters, sizeof(T)) || !sb::aligned_to(membership, 4)) return SB_ERR_MISALIGNED;
   if(n == 0) return SB_OK;
+  if(n / 256 > 0x7fffffffull) return SB_ERR_BAD_ARG;
   sb_device_guard guard(ctx->device);
   // 128-bit loads need every feature row 16-byte aligned: base aligned and the row pitch N*s a multiple of 16
   const bool vector = sb::aligned_to(features, 16) && (n * sizeof(T)) % 16 == 0;
-  const size_t vec = vector ? 16 / sizeof(T) : 1;
-  const size_t blocks = ((n + vec - 1) / vec + 255) / 256;
-  if(blocks > 0x7fffffffull) return SB_ERR_BAD_ARG;
-  if(vector) kmeans_kernel<T, true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(features, clusters, n, nfeatures, nclusters, membership);
-  else kmeans_kernel<T, false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(features, clusters, n, nfeatures, nclusters, membership);
+  if(vector) {
+    if(nfeatures <= 2) kmeans_launch<T, true, 2, 4>(ctx, features, clusters, n, nfeatures, nclusters, membership);
+    else if(nfeatures <= 4) kmeans_launch<T, true, 4, 2>(ctx, features, clusters, n, nfeatures, nclusters, membership);
+    else kmeans_launch<T, true, 0, 1>(ctx, features, clusters, n, nfeatures, nclusters, membership);
+  } else {
+    if(nfeatures <= 4) kmeans_launch<T, false, 4, 4>(ctx, features, clusters, n, nfeatures, nclusters, membership);
+    else kmeans_launch<T, false, 0, 1>(ctx, features, clusters, n, nfeatures, nclusters, membership);
+  }
   SB_CHECK_LAUNCH(ctx);
   return SB_OK;
 }
