@@ -54,8 +54,9 @@ WORKLOADS = {
                 "name": "pattern/reduction + pattern/prefixsum, fp32 and int64, --size=2^28 per GPU (BASELINE configs[1])"},
     "config5": {"legs": (("reduce", "i32", 0), ("scan", "i32", 0)), "log2_total": 33, "scaling": "strong",
                 "name": "pattern/reduction + pattern/prefixsum, int32, --size=2^33 in total, sharded (BASELINE configs[4])"},
-    "config3": {"legs": (("gscan", "i32", 256), ("segscan", "i32", 256)), "log2_per_gpu": 30, "scaling": "weak",
-                "name": "pattern/scan --scan-scope=group + pattern/segmentedscan, int32, --size=2^30 per GPU, --local=256 (BASELINE configs[2], replicas)"},
+    "config3": {"legs": (("gscan", "i32", 256), ("segscan", "i32", 256), ("segscan_flags", "i32", 256)), "log2_per_gpu": 30, "scaling": "weak",
+                "name": "pattern/scan --scan-scope=group + pattern/segmentedscan --no-flags + pattern/segmentedscan (explicit head flags), int32, "
+                        "--size=2^30 per GPU, --local=256 (BASELINE configs[2], replicas)"},
     "config4": {"legs": tuple(("segreduce", "f64", L) for L in (64, 128, 256, 512, 1024)), "log2_per_gpu": 29, "scaling": "weak",
                 "name": "pattern/segmentedreduction fp64, --size=2^29 per GPU, --local 64..1024 (BASELINE configs[3], replicas)"},
 }
@@ -74,6 +75,8 @@ def algorithmic_bytes(op: str, t: str, n: int, L: int = 0) -> int:
         return n * s + s
     if op == "segreduce":
         return n * s + (n // L) * s
+    if op == "segscan_flags":
+        return 2 * n * s + n  # one flag byte per element
     return 2 * n * s  # scan, gscan, segscan
 
 
@@ -321,6 +324,18 @@ class Bench:
                 ctx.check_iota(y, mism, offset=first, kind=0, seg_len=L, rel_tol=rel_tol(t, ntot))
                 return int(mism.item()) == 0
             return run, verify
+        if op == "segscan_flags":
+            # explicit head flags, one byte per element, a head every L (what pattern/segmentedscan generates by default)
+            fl = self.torch.zeros(n, dtype=self.torch.uint8, device=self.dev)
+            fl[::L] = 1
+
+            def run():
+                ctx.segscan(x, y, head_flags=fl)
+
+            def verify():
+                ctx.check_iota(y, mism, offset=first, kind=0, seg_len=L, rel_tol=rel_tol(t, ntot))
+                return int(mism.item()) == 0
+            return run, verify
         if op == "segreduce":
             def run():  # in place: timed on a buffer whose heads already hold sums (same traffic)
                 self.ops.foreach_segreduce(y, L)
@@ -341,7 +356,7 @@ class Bench:
         x = {t: self.empty(t, n) for t in types}
         y = {t: self.empty(t, n) for t in types}
         # the block-cyclic layout belongs to the global reduce / prefix-sum legs; replicas own contiguous shards
-        replicas = any(op in ("gscan", "segscan", "segreduce") for op, _, _ in legs)
+        replicas = any(op in ("gscan", "segscan", "segscan_flags", "segreduce") for op, _, _ in legs)
         for t in types:
             if solo:
                 self.ctx.iota(x[t], offset=0)
@@ -448,6 +463,7 @@ def run_ours(args):
     }
     kern = {"scan": kernels[B.strategy], "reduce": "reduce_kernel<%s, 512, 4> (sb_reduce_%s)" + ("" if world == 1 else (" with the all-reduce fused into its last block (peer mailboxes over NVLink)" if (B.peer is not None and args.reduce_exchange == "fused") else " + NCCL all-reduce of one element")),
             "gscan": "scan_independent_kernel<%s> (sb_scan_%s, group scope)", "segscan": "scan_independent_kernel<%s> (sb_segscan_%s)",
+            "segscan_flags": "flags_tile_heads_kernel + scan_independent_kernel<%s, FLAGS> (sb_segscan_%s, explicit head flags)",
             "segreduce": "segreduce_rows_kernel<%s> (sb_segreduce_%s)"}[dom[0]] % (dom[1], dom[1])
     roofline = {"bound": "hbm", "kernel": kern, "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),

@@ -61,6 +61,10 @@ def worker(args):
             # heads at random positions, mean segment length 256: no tile starts on a head
             fr = (torch.rand(n, device="cuda") < 1.0 / 256).to(torch.uint8)
             cases["segscan_flagsrand"] = (lambda: ctx.segscan(x, y, head_flags=fr), 2 * n * size[t] + n)
+            for dist in (32, 1024, 4096, 65536):
+                if f"segscan_flagsrand{dist}" in args.ops.split(","):
+                    frd = (torch.rand(n, device="cuda") < 1.0 / dist).to(torch.uint8)
+                    cases[f"segscan_flagsrand{dist}"] = ((lambda frd=frd: ctx.segscan(x, y, head_flags=frd)), 2 * n * size[t] + n)
         for name in args.ops.split(","):
             if name not in cases:
                 continue

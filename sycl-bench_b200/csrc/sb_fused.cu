@@ -395,13 +395,19 @@ __global__ void __launch_bounds__(256) kmeans_kernel(const A* __restrict__ featu
           }
         }
       }
+      bool all_set = true;
 #pragma unroll
       for(int c = 0; c < VEC; ++c) {  // kmeans.cpp:72-75
         if(dist[c] < min_dist[c]) {
           min_dist[c] = dist[c];
           index[c] = (int)(g0 + c);  // the reference narrows the size_t global id to int the same way
         }
+        all_set = all_set && min_dist[c] < (A)3.402823466e+38f;
       }
+      // Once a distance has been below FLT_MAX the stored value is g whatever the remaining clusters give (`index = gid`
+      // again): stop.  For ordinary data that is after the first cluster — a third of the arithmetic at nclusters = 3,
+      // which matters for fp64 (21 double operations per point against 20 bytes of traffic).
+      if(all_set) break;
     }
     if(VECTOR && cnt[u] == VEC && (reinterpret_cast<uintptr_t>(membership + g0) & (4 * VEC - 1)) == 0) {
       if constexpr(VEC == 4) *reinterpret_cast<int4*>(membership + g0) = make_int4(index[0], index[1], index[2], index[3]);

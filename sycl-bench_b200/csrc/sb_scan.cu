@@ -159,7 +159,7 @@ __device__ __forceinline__ A lookback(const typename Desc<A>::word* desc, long l
 // round look-back (persistent kernel), see the header comment
 template <typename A, int MODE, typename Idle>
 __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, const typename Desc<A>::word* rdesc, long long tile,
-    long long G, uint32_t epoch, const A* __restrict__ seed, Deadline& dl, unsigned* err, Idle on_idle, bool early = false) {
+    long long G, uint32_t epoch, const A* __restrict__ seed, Deadline& dl, unsigned* err, Idle on_idle) {
   constexpr int U = SCAN_WINDOW;
   const int lane = sb::lane_id();
   const long long r = tile / G;
@@ -198,7 +198,7 @@ __device__ __forceinline__ A lookback_round(const typename Desc<A>::word* desc, 
     // critical path.  Hence only where it measured faster.
     for(;;) {
       bool missing = false;
-      if(MODE == MODE_FLAGS && SB_SCAN_SEG_EARLY && (sizeof(A) == 4 || early)) {
+      if(MODE == MODE_FLAGS && sizeof(A) == 4 && SB_SCAN_SEG_EARLY) {
         int stop_u = U;  // window of the nearest head seen so far (warp-uniform)
 #pragma unroll
         for(int u = 0; u < U; ++u) {
@@ -349,18 +349,18 @@ template <typename A, int MODE, int K, int NW>
 __global__ void __launch_bounds__((NW + 2) * 32, SB_WS_MINB)
 scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* __restrict__ flags,
     const A* __restrict__ seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, long long num_tiles, int flags_in_ring,
-    unsigned* err, unsigned long long timeout_ns, const unsigned long long* gate, unsigned long long gate_seq, int gate_want, int sp_allowed) {
+    unsigned* err, unsigned long long timeout_ns, const unsigned long long* gate, unsigned long long gate_seq, int gate_want) {
   using C = TileCfg<A, NW, K>;
   constexpr int VEC = C::VEC;
   constexpr int STAGE_BYTES = ws_stage_bytes<A, MODE, K, NW>();
   extern __shared__ __align__(128) unsigned char ring[];  // WS_STAGES x STAGE_BYTES
   __shared__ __align__(8) unsigned long long full_bar[WS_STAGES], empty_bar[WS_STAGES], agg_bar[WS_NSLOT], prefix_bar[WS_NSLOT];
   if(gate && (int)(*gate == gate_seq) != gate_want) return;  // explicit flags: the other kernel of the pair runs (flags_tile_heads_kernel)
-  // SINGLE-PASS tiles (explicit flags whose heads are dense, second verdict of the check kernel): with a head in (almost) every
-  // tile a look-back ends at the neighbouring tile, so there is no chain to hide and running phase A ahead of phase B only
-  // costs a second pass over the ring.  The tile is scanned once: pass 1 of phase B yields the warp sums, the look-back warp
-  // publishes and resolves the prefix while the tile waits in registers (the stage is already released), pass 2 stores.
-  const bool sp = MODE == MODE_FLAGS && gate && sp_allowed && gate[1] != gate_seq;
+  // (Measured and removed: SINGLE-PASS tiles for dense explicit flags — no phase A, the warp sums come out of pass 1 of phase B
+  // and the tile waits in registers for a look-back that ends at the neighbouring tile.  One pass over the ring instead of
+  // two, yet 18-25 % SLOWER with random heads at mean distance 32 ... 1024 (int32 4.34 -> 3.25, int64 3.08 -> 2.53 TB/s,
+  // profiles/r02_ops_v15_single_pass_ab.jsonl): pass 1 -> publish -> look-back -> pass 2 is then a serial chain per tile with
+  // the workers idle in between, whereas phase A of the next tile overlaps it in the two-phase form.)
   __shared__ A s_wagg[WS_NSLOT][NW];
   __shared__ int s_wflag[WS_NSLOT][NW];
   __shared__ A s_tprefix[WS_NSLOT];
@@ -469,7 +469,7 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
       cur = i;
       publish(i);
       A p = A(0);
-      if(!on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed, dl_seg, err, [&] { publish(-1); }, sp);
+      if(!on_head) p = lookback_round<A, MODE>(desc, rdesc, tile, G, epoch, seed, dl_seg, err, [&] { publish(-1); });
       if(lane == 0) {
         if((tile + 1) % G == 0) {
           const A tile_agg = s_tagg[slot];  // written by this lane in publish()
@@ -534,8 +534,6 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         if(lazy_cur) {
           lazy_hist |= 1u;
           if(lane == 0) mbar_arrive(smem_u32(&agg_bar[slot]));  // nothing to contribute: wakes the look-back warp
-        } else if(sp) {
-          // single-pass tile: the warp sums come out of pass 1 of phase B
         } else {
           const size_t wbase = (size_t)tile * C::TILE + (size_t)warp * C::WCHUNK + (size_t)lane * VEC;
           const bool full_tile = (size_t)(tile + 1) * C::TILE <= n;
@@ -568,7 +566,7 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
         const bool lazy = (lazy_hist >> WS_DEPTH) & 1u;
         A v[K][VEC];
         unsigned hf[K];
-        if(lazy || sp) mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(b / WS_STAGES) & 1u);  // phase A did not wait for the data
+        if(lazy) mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)(b / WS_STAGES) & 1u);  // phase A did not wait for the data
         if(MODE == MODE_FLAGS && flags_in_ring && full_tile)
           tile_head_flags_ring<A, K>(hf, ring + (size_t)stage * STAGE_BYTES + C::TILE_BYTES + (size_t)warp * C::WCHUNK, wbase);
         else
@@ -594,12 +592,6 @@ scan_ws_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg_len, siz
           }
           mbar_wait(smem_u32(&xchg_bar), lazy_done & 1u);
           ++lazy_done;
-        } else if(sp) {
-          if(lane == 0) {
-            s_wagg[slot][warp] = warp_agg;
-            s_wflag[slot][warp] = warp_has_head ? 1 : 0;
-            mbar_arrive(smem_u32(&agg_bar[slot]));  // the look-back warp publishes the tile now
-          }
         }
         // all warps' pairs of this tile (and, with look-back, the tile prefix) are complete
         const uint32_t par = (uint32_t)(b / WS_NSLOT) & 1u;
@@ -744,49 +736,11 @@ scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg
 // The host cannot know without a round trip, so it launches this check (one byte per tile), then BOTH scan kernels, each
 // of which leaves at once unless the verdict names it.  Verdict: *gate == seq  <=>  some tile of check number `seq` does NOT
 // start on a head (sequence numbers only grow, so atomicMax never needs a reset).
-__global__ void __launch_bounds__(256) flags_tile_heads_kernel(const uint8_t* __restrict__ flags, long long num_tiles, size_t tile, size_t n,
+__global__ void __launch_bounds__(256) flags_tile_heads_kernel(const uint8_t* __restrict__ flags, long long num_tiles, size_t tile,
     unsigned long long* gate, unsigned long long seq) {
   const long long t = 1 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int bad = t < num_tiles && __ldg(flags + (size_t)t * tile) == 0 ? 1 : 0;
-  // second verdict (gate[1] == seq  <=>  the heads are NOT dense somewhere): the first 64 flag bytes of every tile are a
-  // sample of the head density; a block (256 tiles) calls its stretch dense when the mean head distance of its sample is
-  // at most a quarter of a tile, i.e. nearly every tile holds a head (see the single-pass tiles of scan_ws_kernel)
-  constexpr int SAMPLE = 64;
-  int heads = 0, bytes = 0;
-  if(t < num_tiles) {
-    const size_t base = (size_t)t * tile;
-    if(base + SAMPLE <= n && (reinterpret_cast<uintptr_t>(flags + base) & 15) == 0) {
-#pragma unroll
-      for(int k = 0; k < SAMPLE / 16; ++k) {
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(flags + base) + k);
-        heads += __popc(__vcmpne4(w.x, 0u) & 0x01010101u) + __popc(__vcmpne4(w.y, 0u) & 0x01010101u) +
-                 __popc(__vcmpne4(w.z, 0u) & 0x01010101u) + __popc(__vcmpne4(w.w, 0u) & 0x01010101u);
-      }
-      bytes = SAMPLE;
-    } else {
-      for(int k = 0; k < SAMPLE && base + k < n; ++k) {
-        heads += __ldg(flags + base + k) != 0 ? 1 : 0;
-        ++bytes;
-      }
-    }
-  }
-  heads = __reduce_add_sync(SB_FULL_MASK, heads);
-  bytes = __reduce_add_sync(SB_FULL_MASK, bytes);
-  __shared__ int s_heads[8], s_bytes[8];
-  if((threadIdx.x & 31) == 0) {
-    s_heads[threadIdx.x >> 5] = heads;
-    s_bytes[threadIdx.x >> 5] = bytes;
-  }
-  const int any_bad = __syncthreads_or(bad);
-  if(threadIdx.x == 0) {
-    long long h = 0, by = 0;
-    for(int w = 0; w < 8; ++w) {
-      h += s_heads[w];
-      by += s_bytes[w];
-    }
-    if(any_bad) atomicMax(gate, seq);
-    if(h * (long long)tile < 4 * by) atomicMax(gate + 1, seq);  // mean distance by / h > tile / 4: sparse
-  }
+  if(__syncthreads_or(bad) && threadIdx.x == 0) atomicMax(gate, seq);
 }
 
 // co-resident CTAs per SM of a persistent kernel instantiation.  The shared-memory opt-in is a per-device
@@ -844,12 +798,9 @@ int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t 
   // launch) — the forward-progress condition of the static round-robin look-back.  No grid barrier is used.
   unsigned* err = ctx->err_dev;
   unsigned long long timeout_ns = sb_peer_timeout_ns();
-  // SB_SCAN_FLAGS_SP=0: explicit flags never take single-pass tiles (A/B measurements)
-  static const int sp_env = !(getenv("SB_SCAN_FLAGS_SP") && getenv("SB_SCAN_FLAGS_SP")[0] == '0');
-  int sp_allowed = sp_env;
   void* args[] = {(void*)&in, (void*)&out, (void*)&n, (void*)&exclusive, (void*)&seg_len, (void*)&seg_mask, (void*)&flags, (void*)&seed,
       (void*)&desc, (void*)&epoch, (void*)&use_lookback, (void*)&num_tiles, (void*)&flags_in_ring, (void*)&err, (void*)&timeout_ns,
-      (void*)&gate, (void*)&gate_seq, (void*)&gate_want, (void*)&sp_allowed};
+      (void*)&gate, (void*)&gate_seq, (void*)&gate_want};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)scan_ws_kernel<A, MODE, K, NW>, dim3((unsigned)grid), dim3(WS_THREADS), args, smem, ctx->stream);
   if(e != cudaSuccess) return (int)e;
   return SB_OK;
@@ -943,7 +894,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
       if(gate_enabled && use_lookback && tiles >= 64) {
         unsigned long long* g = ctx->scan_ticket + 16;  // byte 128 of the ctx's 256-byte ticket block (zeroed at creation)
         seq = ++ctx->flags_gate_seq;
-        flags_tile_heads_kernel<<<(unsigned)((tiles + 254) / 256), 256, 0, ctx->stream>>>(flags, (long long)tiles, tile, n, g, seq);
+        flags_tile_heads_kernel<<<(unsigned)((tiles + 254) / 256), 256, 0, ctx->stream>>>(flags, (long long)tiles, tile, g, seq);
         gate = g;
         // (64-bit types keep the 14-worker tile here too: 15 workers x 6 rows x 64 elements is not a multiple of 256)
         if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, seq, 0);

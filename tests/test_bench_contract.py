@@ -47,6 +47,6 @@ def test_bench_line_contract():
     c5 = line["config5"]
     assert c5["verified"] and set(c5["per_leg"]) == {"reduce_i32", "scan_i32"} and c5["elements_total"] == 1 << 24
     rp = line["replicas"]
-    assert rp["verified"] and set(rp["config3"]["per_leg"]) == {"gscan_i32_L256", "segscan_i32_L256"}
+    assert rp["verified"] and set(rp["config3"]["per_leg"]) == {"gscan_i32_L256", "segscan_i32_L256", "segscan_flags_i32_L256"}
     assert set(rp["config4"]["per_leg"]) == {f"segreduce_f64_L{L}" for L in (64, 128, 256, 512, 1024)}
     assert e["roofline"]["bound"] == "pcie" and 0 < e["roofline"]["frac"] <= 1.5

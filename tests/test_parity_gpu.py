@@ -232,14 +232,15 @@ def test_segscan_explicit_flags(ctx, O, t, density, exclusive):
 
 
 @pytest.mark.parametrize("t", ALL4)
-@pytest.mark.parametrize("case", ["every256", "every256_one_tile_open", "every3", "random"])
+@pytest.mark.parametrize("case", ["every256", "every256_one_tile_open", "every3", "random", "random1000", "random3000", "random8000",
+                                  "dense_then_sparse", "tile_heads_half"])
 @pytest.mark.parametrize("exclusive", [False, True])
 def test_segscan_explicit_flags_gated_pair(ctx, O, t, case, exclusive):
     """From 64 tiles on, explicit flags launch a check kernel and BOTH persistent kernels, gated by the check's verdict
     (csrc/sb_scan.cu: flags_tile_heads_kernel): the independent-tile kernel when every tile starts on a head, the
     look-back kernel otherwise.  Both verdicts, repeated launches on one ctx (the gated-off kernel must leave the
     tile ticket where the host mirror expects it), a ragged last tile."""
-    n = (1 << 20) + 777
+    n = (1 << 21) + 777
     flags = np.zeros(n, dtype=np.uint8)
     if case.startswith("every256"):
         flags[::256] = 1
@@ -249,8 +250,22 @@ def test_segscan_explicit_flags_gated_pair(ctx, O, t, case, exclusive):
             flags[12288 * 3] = 0
     elif case == "every3":
         flags[::3] = 1
-    else:
+    elif case == "random":
         flags[np.random.default_rng(5).random(n) < 1e-4] = 1
+    elif case.startswith("random"):
+        # mean head distance 1000 / 3000 / 8000: from several heads per tile to tiles without any (the look-back of the
+        # 32-bit types stops at the nearest tile holding a head)
+        flags[np.random.default_rng(6).random(n) < 1.0 / int(case[6:])] = 1
+    elif case == "dense_then_sparse":
+        flags[: n // 2][np.random.default_rng(7).random(n // 2) < 0.01] = 1
+        flags[n // 2 + 12345] = 1
+    else:
+        # a head right behind the first element of every other tile (of either tile size) and nowhere else: no tile starts
+        # on a head, half of the tiles hold none and their look-backs go further than the neighbour
+        rng = np.random.default_rng(8)
+        for tile in (5376, 12288):
+            starts = np.arange(tile, n - 2, tile)
+            flags[starts[rng.random(starts.size) < 0.5] + 1] = 1
     hx = rand_input(t, n)
     x, f = dev(hx), dev(flags)
     for rep in range(3):
