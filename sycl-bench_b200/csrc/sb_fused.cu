@@ -306,8 +306,8 @@ int linreg_error_impl(sb_ctx* ctx, const T* x, const T* y, const T* alpha, const
 // the cluster's (`index = gid`, :74): membership[g] = g as soon as one distance is below the running minimum, which starts
 // at FLT_MAX, and 0 otherwise (all distances >= FLT_MAX or NaN).  Kept literally.  A pure map: nfeatures*N*s bytes in,
 // 4*N out, HBM-bound; a thread owns one 16-byte vector of points per feature row (128-bit coalesced loads, 128-bit or
-// 2 x 128-bit stores), the cluster table sits in shared memory.  Distances are summed in T in the reference's order with
-// one rounding per operation.
+// 2 x 128-bit stores), the cluster table sits in shared memory.  Distances are summed in T in the reference's order
+// (d*d + dist contracted to one fma, like the reference's own -ffast-math build; it only matters within an ulp of FLT_MAX).
 constexpr int KM_MAX_TABLE = 2048;  // cluster-table elements kept in shared memory
 
 // NFR > 0: the point's features (nfeatures <= NFR) are read once and stay in registers over the cluster loop, U vectors of
@@ -363,10 +363,12 @@ __global__ void __launch_bounds__(256) kmeans_kernel(const A* __restrict__ featu
     const size_t g0 = (v0 + (size_t)u * 256) * VEC;
     A min_dist[VEC];
     int index[VEC];
+    bool set[VEC];
 #pragma unroll
     for(int c = 0; c < VEC; ++c) {
       min_dist[c] = (A)3.402823466e+38f;  // FLT_MAX, kmeans.cpp:66
       index[c] = 0;
+      set[c] = c >= cnt[u];  // (components past the end of the array count as decided)
     }
     for(int k = 0; k < nclusters; ++k) {
       A dist[VEC];
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(256) kmeans_kernel(const A* __restrict__ featu
 #pragma unroll
             for(int c = 0; c < VEC; ++c) {
               const A d = sub_rn<A>(f[u][l][c], cl);
-              dist[c] += mul_rn<A>(d, d);
+              dist[c] = fma(d, d, dist[c]);  // (contracted, as the reference's own -ffast-math build does)
             }
           }
         }
@@ -395,15 +397,17 @@ __global__ void __launch_bounds__(256) kmeans_kernel(const A* __restrict__ featu
           }
         }
       }
-      bool all_set = true;
 #pragma unroll
       for(int c = 0; c < VEC; ++c) {  // kmeans.cpp:72-75
         if(dist[c] < min_dist[c]) {
           min_dist[c] = dist[c];
           index[c] = (int)(g0 + c);  // the reference narrows the size_t global id to int the same way
+          set[c] = true;
         }
-        all_set = all_set && min_dist[c] < (A)3.402823466e+38f;
       }
+      bool all_set = true;
+#pragma unroll
+      for(int c = 0; c < VEC; ++c) all_set = all_set && set[c];
       // Once a distance has been below FLT_MAX the stored value is g whatever the remaining clusters give (`index = gid`
       // again): stop.  For ordinary data that is after the first cluster — a third of the arithmetic at nclusters = 3,
       // which matters for fp64 (21 double operations per point against 20 bytes of traffic).

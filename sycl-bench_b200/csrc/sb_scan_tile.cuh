@@ -234,6 +234,8 @@ __device__ __forceinline__ void warp_reduce_rows(const A (&v)[K][16 / sizeof(A)]
       return;
     }
   }
+#ifdef SB_SCAN_PHASEA_PER_ROW
+  // previous form: one warp sum per row (K x 5 shuffles), restarted at the last head of a row
   A run = A(0);
   bool runf = false;
 #pragma unroll
@@ -253,6 +255,30 @@ __device__ __forceinline__ void warp_reduce_rows(const A (&v)[K][16 / sizeof(A)]
   }
   agg = run;
   has_head = runf;
+#else
+  // Only what follows the LAST head of the chunk counts.  Its place (row jl, lane ll) comes out of K ballots; every lane then
+  // adds up the rows behind it — of row jl only the lanes from ll on, whose partial `s` already starts at their own last
+  // head — and ONE warp sum finishes: 5 shuffles per chunk instead of 5 per row.
+  A s[K];
+  int jl = -1, ll = 0;
+#pragma unroll
+  for(int j = 0; j < K; ++j) {
+    s[j] = A(0);
+#pragma unroll
+    for(int c = 0; c < VEC; ++c) s[j] = clear_if(s[j], head_mask(hf[j], c)) + v[j][c];
+    const unsigned hm = __ballot_sync(SB_FULL_MASK, hf[j] != 0u);
+    if(hm) {
+      jl = j;
+      ll = 31 - __clz(hm);
+    }
+  }
+  A acc = A(0);
+#pragma unroll
+  for(int j = 0; j < K; ++j)
+    if(j > jl || (j == jl && lane >= ll)) acc += s[j];
+  agg = sb::warp_sum<A>(acc);
+  has_head = jl >= 0;
+#endif
 }
 
 // pass 1: thread partials -> per-row warp segmented scan.  The K row scans are independent shuffle
