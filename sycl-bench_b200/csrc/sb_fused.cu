@@ -332,18 +332,32 @@ __global__ void __launch_bounds__(256) kmeans_kernel(const A* __restrict__ featu
     cnt[u] = g0 >= n ? 0 : (n - g0 < (size_t)VEC) ? (int)(n - g0) : VEC;
   }
   if(NFR > 0) {
+    // A block whose 256 * U vectors all lie inside the array (every block but the last) loads without per-thread guards:
+    // with the guard the compiler merged the vector and the scalar path through predicated moves behind EVERY load, and
+    // the U * nfeatures loads of a thread waited for one another (ncu, fp64: 71 % of the warp samples on those moves,
+    // 3.8 TB/s of DRAM traffic; profiles/r02_ncu_kmeans_f64.txt).
+    const bool full_block = ((size_t)blockIdx.x + 1) * (256 * U) * VEC <= n;
+    if(VECTOR && full_block) {
+      sb::Vec<A> t[U][NF];
 #pragma unroll
-    for(int u = 0; u < U; ++u) {
-      const size_t g0 = (v0 + (size_t)u * 256) * VEC;
+      for(int u = 0; u < U; ++u)
 #pragma unroll
-      for(int l = 0; l < NF; ++l) {
-        if(l < nfeatures) {
-          const A* row = features + (size_t)l * n + g0;
-          if(VECTOR && cnt[u] == VEC) {
-            const sb::Vec<A> t = sb::ldg_nc_ordered<A>(row);
+        for(int l = 0; l < NF; ++l)
+          if(l < nfeatures) t[u][l] = sb::ldg_nc_ordered<A>(features + (size_t)l * n + (v0 + (size_t)u * 256) * VEC);
 #pragma unroll
-            for(int c = 0; c < VEC; ++c) f[u][l][c] = t.v[c];
-          } else {
+      for(int u = 0; u < U; ++u)
+#pragma unroll
+        for(int l = 0; l < NF; ++l)
+#pragma unroll
+          for(int c = 0; c < VEC; ++c) f[u][l][c] = t[u][l].v[c];
+    } else {
+#pragma unroll
+      for(int u = 0; u < U; ++u) {
+        const size_t g0 = (v0 + (size_t)u * 256) * VEC;
+#pragma unroll
+        for(int l = 0; l < NF; ++l) {
+          if(l < nfeatures) {
+            const A* row = features + (size_t)l * n + g0;
 #pragma unroll
             for(int c = 0; c < VEC; ++c) f[u][l][c] = c < cnt[u] ? __ldg(row + c) : A(0);
           }

@@ -234,51 +234,61 @@ __device__ __forceinline__ void warp_reduce_rows(const A (&v)[K][16 / sizeof(A)]
       return;
     }
   }
+  // Two forms.  PER CHUNK (second branch), measured at 2^28 against PER ROW (profiles/r02_ops_v16_phasea_ab.jsonl): +13-18 % for
+  // 64-bit types with explicit flags at random positions (int64 3.14 -> 3.66 TB/s), +6.5 % for 64-bit implicit heads at
+  // L = 65536, 0 ... +10 % for 32-bit explicit flags — but -4.5 ... -6 % for 32-bit implicit heads (the K partials push the
+  // 18-worker instantiation over its 96 registers), which therefore keep the per-row form.
+  constexpr bool PER_ROW =
 #ifdef SB_SCAN_PHASEA_PER_ROW
-  // previous form: one warp sum per row (K x 5 shuffles), restarted at the last head of a row
-  A run = A(0);
-  bool runf = false;
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    A s = A(0);
-    const bool f = hf[j] != 0u;
-#pragma unroll
-    for(int c = 0; c < VEC; ++c) s = clear_if(s, head_mask(hf[j], c)) + v[j][c];
-    const unsigned hm = __ballot_sync(SB_FULL_MASK, f);
-    if(hm) {
-      const int hl = 31 - __clz(hm);
-      run = sb::warp_sum<A>(lane >= hl ? s : A(0));
-      runf = true;
-    } else {
-      run += sb::warp_sum<A>(s);
-    }
-  }
-  agg = run;
-  has_head = runf;
+      true;
 #else
-  // Only what follows the LAST head of the chunk counts.  Its place (row jl, lane ll) comes out of K ballots; every lane then
-  // adds up the rows behind it — of row jl only the lanes from ll on, whose partial `s` already starts at their own last
-  // head — and ONE warp sum finishes: 5 shuffles per chunk instead of 5 per row.
-  A s[K];
-  int jl = -1, ll = 0;
-#pragma unroll
-  for(int j = 0; j < K; ++j) {
-    s[j] = A(0);
-#pragma unroll
-    for(int c = 0; c < VEC; ++c) s[j] = clear_if(s[j], head_mask(hf[j], c)) + v[j][c];
-    const unsigned hm = __ballot_sync(SB_FULL_MASK, hf[j] != 0u);
-    if(hm) {
-      jl = j;
-      ll = 31 - __clz(hm);
-    }
-  }
-  A acc = A(0);
-#pragma unroll
-  for(int j = 0; j < K; ++j)
-    if(j > jl || (j == jl && lane >= ll)) acc += s[j];
-  agg = sb::warp_sum<A>(acc);
-  has_head = jl >= 0;
+      MODE == MODE_IMPLICIT && sizeof(A) == 4;
 #endif
+  if(PER_ROW) {
+    // one warp sum per row (K x 5 shuffles), restarted at the last head of a row
+    A run = A(0);
+    bool runf = false;
+#pragma unroll
+    for(int j = 0; j < K; ++j) {
+      A s = A(0);
+      const bool f = hf[j] != 0u;
+#pragma unroll
+      for(int c = 0; c < VEC; ++c) s = clear_if(s, head_mask(hf[j], c)) + v[j][c];
+      const unsigned hm = __ballot_sync(SB_FULL_MASK, f);
+      if(hm) {
+        const int hl = 31 - __clz(hm);
+        run = sb::warp_sum<A>(lane >= hl ? s : A(0));
+        runf = true;
+      } else {
+        run += sb::warp_sum<A>(s);
+      }
+    }
+    agg = run;
+    has_head = runf;
+  } else {
+    // Only what follows the LAST head of the chunk counts.  Its place (row jl, lane ll) comes out of K ballots; every lane
+    // then adds up the rows behind it — of row jl only the lanes from ll on, whose partial `s` already starts at their own
+    // last head — and ONE warp sum finishes: 5 shuffles per chunk instead of 5 per row.
+    A s[K];
+    int jl = -1, ll = 0;
+#pragma unroll
+    for(int j = 0; j < K; ++j) {
+      s[j] = A(0);
+#pragma unroll
+      for(int c = 0; c < VEC; ++c) s[j] = clear_if(s[j], head_mask(hf[j], c)) + v[j][c];
+      const unsigned hm = __ballot_sync(SB_FULL_MASK, hf[j] != 0u);
+      if(hm) {
+        jl = j;
+        ll = 31 - __clz(hm);
+      }
+    }
+    A acc = A(0);
+#pragma unroll
+    for(int j = 0; j < K; ++j)
+      if(j > jl || (j == jl && lane >= ll)) acc += s[j];
+    agg = sb::warp_sum<A>(acc);
+    has_head = jl >= 0;
+  }
 }
 
 // pass 1: thread partials -> per-row warp segmented scan.  The K row scans are independent shuffle

@@ -94,3 +94,34 @@ def test_linreg_recovers_an_exact_line(O, t):
     mx, my = sx / n, sy / n
     b1 = (sxy - mx * my) / (sxx - mx * mx)
     assert abs(float(out[4]) - b1) <= 1e-5 * abs(b1) and abs(float(out[5]) - (my - b1 * mx)) <= 1e-4
+
+
+@settings(max_examples=25, deadline=None)
+@given(seed=st.integers(0, 2**31), n=st.integers(1, 300), t=st.sampled_from(["f32", "f64"]))
+def test_lin_reg_error_on_exactly_representable_points(O, seed, n, t):
+    """Points and candidates on a coarse binary grid: every product and partial sum of the reference's loop
+    (lin_reg_error.cpp:64-77) is exact in both types, so the restatement must equal the integer arithmetic bit for bit."""
+    rng = np.random.default_rng(seed)
+    dt = np.float32 if t == "f32" else np.float64
+    x, y, a, b = [(rng.integers(-8, 9, n) / 4.0).astype(dt) for _ in range(4)]
+    got = O.lin_reg_error(t, x, y, a, b)
+    xi, yi, ai, bi = [np.round(v.astype(np.float64) * 4).astype(np.int64) for v in (x, y, a, b)]
+    for g in range(n):
+        e = ai[g] * xi + 4 * bi[g] - 4 * yi  # 16 * ((a x + b) - y)
+        assert float(got[g]) == float((e * e).sum()) / 256.0
+
+
+@settings(max_examples=25, deadline=None)
+@given(seed=st.integers(0, 2**31), n=st.integers(1, 200), nf=st.integers(0, 5), nc=st.integers(0, 4), t=st.sampled_from(["f32", "f64"]))
+def test_kmeans_membership_is_the_point_index_or_zero(O, seed, n, nf, nc, t):
+    """kmeans.cpp:61-79 stores `gid` when a distance is below FLT_MAX and 0 otherwise — never a cluster index."""
+    rng = np.random.default_rng(seed)
+    dt = np.float32 if t == "f32" else np.float64
+    f = rng.standard_normal(max(nf * n, 1)).astype(dt)
+    f[rng.random(f.size) < 0.1] = np.nan
+    c = rng.standard_normal(max(nf * nc, 1)).astype(dt)
+    m = O.kmeans(t, f, c, n, nf, nc)
+    for g in range(n):
+        dists = [sum((float(f[l * n + g]) - float(c[i * nf + l])) ** 2 for l in range(nf)) for i in range(nc)]
+        finite = any(d < 3.402823466e38 for d in dists)  # NaN compares false
+        assert m[g] == (g if finite else 0)
