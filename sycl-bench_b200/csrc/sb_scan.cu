@@ -732,7 +732,7 @@ scan_independent_kernel(const A* in, A* out, size_t n, int exclusive, size_t seg
 // ---- explicit head flags: does every tile start on a head? ----------------------------------------------------------
 // If so (the benchmark's own flags: a head every `--local` elements, and the tile is a multiple of that) no tile needs
 // anything from another tile and the independent-tile kernel does the job without descriptors, look-back warp and phase A
-// (2^28 elements: int32 5.04 -> 6.37, fp32 5.24 -> 6.40, int64 4.08 -> 5.03, fp64 4.24 -> 5.65 TB/s).
+// (2^28 elements: int32 5.04 -> 6.58, fp32 5.24 -> 6.59, int64 4.08 -> 6.65, fp64 4.24 -> 6.77 TB/s).
 // The host cannot know without a round trip, so it launches this check (one byte per tile), then BOTH scan kernels, each
 // of which leaves at once unless the verdict names it.  Verdict: *gate == seq  <=>  some tile of check number `seq` does NOT
 // start on a head (sequence numbers only grow, so atomicMax never needs a reset).
@@ -764,13 +764,21 @@ int resident_ctas_per_sm(OccupancyCache& cache, int device, Kern kern, int threa
 }
 
 // rows per worker warp: 8 (64 KB tiles); 6 with explicit flags so that 3 stages of data + flag bytes fit in 227 KB
-template <int MODE> struct ws_rows { static constexpr int K = MODE == MODE_FLAGS ? (WS_K * 3) / 4 : WS_K; };
+// (64-bit types carry half as many flag bytes per tile byte: 14 workers x 8 rows = 56 KB + 7 KB of flags per stage fit three times,
+//  so they keep 8 rows: the benchmark's flags int64 5.17 -> 6.65, fp64 5.84 -> 6.77 TB/s, random heads +4-8 %
+//  (profiles/r02_ops_v18_flags_k8_64bit_ab.jsonl; SB_WS_FLAGS_K64=6 builds the previous 6-row tiles for A/B)
+#ifndef SB_WS_FLAGS_K64
+#define SB_WS_FLAGS_K64 SB_WS_K
+#endif
+template <int MODE, int BYTES = 4> struct ws_rows {
+  static constexpr int K = MODE == MODE_FLAGS ? (BYTES == 8 ? SB_WS_FLAGS_K64 : (WS_K * 3) / 4) : WS_K;
+};
 
 template <typename A, int MODE, int NW>
 int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* flags,
     const A* seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, size_t tiles, const unsigned long long* gate = nullptr,
     unsigned long long gate_seq = 0, int gate_want = 0) {
-  constexpr int K = ws_rows<MODE>::K;
+  constexpr int K = ws_rows<MODE, (int)sizeof(A)>::K;
   constexpr size_t smem = (size_t)WS_STAGES * ws_stage_bytes<A, MODE, K, NW>();
   constexpr int WS_THREADS = (NW + 2) * 32;
   static OccupancyCache ws_cache, ind_cache;
@@ -842,7 +850,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   // by a wide margin (L = 16384 on the look-back path measured 3.0 TB/s against 5.5-6.6 for independent tiles)
   const bool mid = mode == MODE_IMPLICIT && sizeof(A) == 8 && !narrow && sb::is_pow2(seg_len) && TileCfg<A, WS_NW, WS_K>::TILE % seg_len == 0;
   const bool lb64 = lb64_enabled && sizeof(A) == 8 && (mode == MODE_FLAGS || (mode == MODE_IMPLICIT && !narrow && !mid));
-  const size_t ws_tile = mode == MODE_FLAGS ? (lb64 ? TileCfg<A, WS_NW_LB64, ws_rows<MODE_FLAGS>::K>::TILE : TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS>::K>::TILE)
+  const size_t ws_tile = mode == MODE_FLAGS ? (lb64 ? TileCfg<A, WS_NW_LB64, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE : TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE)
                          : wide ? wide_tile : narrow ? narrow_tile : lb64 ? TileCfg<A, WS_NW_LB64, WS_K>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
   const size_t simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
   const bool use_ws = aligned && n >= 4 * ws_tile;
