@@ -87,7 +87,7 @@ constexpr int WS_NW_WIDE = SB_WS_NW_WIDE;
 #endif
 constexpr int WS_NW_NARROW = SB_WS_NW_NARROW;
 #ifndef SB_WS_NW_FLAGS
-#define SB_WS_NW_FLAGS SB_WS_NW  // worker warps of the explicit-flag instantiation
+#define SB_WS_NW_FLAGS 14  // worker warps of the explicit-flag instantiations: 14 + producer + look-back = 16 warps, 128 registers
 #endif
 constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
 // Measured and NOT kept for this kernel (profiles/r02_ops_v6_wprefix_ab.jsonl, r02_ops_v8_totals_ab.jsonl):
@@ -763,15 +763,22 @@ int resident_ctas_per_sm(OccupancyCache& cache, int device, Kern kern, int threa
   return nb;
 }
 
-// rows per worker warp: 8 (64 KB tiles); 6 with explicit flags so that 3 stages of data + flag bytes fit in 227 KB
+// rows per worker warp: 8.  Explicit flags ran 6 rows (16 workers) so that 3 stages of data + flag bytes fit in 227 KB; with
+// 14 workers 8 rows fit for every type:
 // (64-bit types carry half as many flag bytes per tile byte: 14 workers x 8 rows = 56 KB + 7 KB of flags per stage fit three times,
 //  so they keep 8 rows: the benchmark's flags int64 5.17 -> 6.65, fp64 5.84 -> 6.77 TB/s, random heads +4-8 %
 //  (profiles/r02_ops_v18_flags_k8_64bit_ab.jsonl; SB_WS_FLAGS_K64=6 builds the previous 6-row tiles for A/B)
 #ifndef SB_WS_FLAGS_K64
 #define SB_WS_FLAGS_K64 SB_WS_K
 #endif
+// (32-bit types: 14 workers x 8 rows = 56 KB + 14 KB of flags per stage fit three times as well; against 16 workers x 6 rows
+//  random heads gain 8-9 % (int32 4.42 -> 4.77 TB/s at mean distance 256), the benchmark's flags are unchanged (6.55-6.9):
+//  profiles/r02_ops_v19_flags32_14x8_ab.jsonl.  -DSB_WS_NW_FLAGS=16 -DSB_WS_FLAGS_K32=6 builds the previous shape.)
+#ifndef SB_WS_FLAGS_K32
+#define SB_WS_FLAGS_K32 SB_WS_K
+#endif
 template <int MODE, int BYTES = 4> struct ws_rows {
-  static constexpr int K = MODE == MODE_FLAGS ? (BYTES == 8 ? SB_WS_FLAGS_K64 : (WS_K * 3) / 4) : WS_K;
+  static constexpr int K = MODE == MODE_FLAGS ? (BYTES == 8 ? SB_WS_FLAGS_K64 : SB_WS_FLAGS_K32) : WS_K;
 };
 
 template <typename A, int MODE, int NW>
