@@ -108,6 +108,11 @@ constexpr int WS_NW_FLAGS = SB_WS_NW_FLAGS;
 #define SB_WS_NW_LB64 14  // 64-bit types, segmented modes with look-back: 14 + 2 = 16 warps -> 128 registers per thread
 #endif
 constexpr int WS_NW_LB64 = SB_WS_NW_LB64;
+#ifndef SB_WS_K_LB64
+#define SB_WS_K_LB64 8  // rows per warp of that instantiation with implicit heads.  10 rows (70 KB tiles, 3 stages = 210 KB) measured
+                        // -1 ... -7 % except L = 2^20 (+3 %): not the tile size (profiles/r02_ops_v20_lb64_k10_ab.jsonl)
+#endif
+constexpr int WS_K_LB64 = SB_WS_K_LB64;
 #ifndef SB_SCAN_SEG_EARLY
 #define SB_SCAN_SEG_EARLY 1  // explicit flags, 32-bit: the look-back waits only for the descriptors up to the nearest head
 #endif
@@ -781,11 +786,11 @@ template <int MODE, int BYTES = 4> struct ws_rows {
   static constexpr int K = MODE == MODE_FLAGS ? (BYTES == 8 ? SB_WS_FLAGS_K64 : SB_WS_FLAGS_K32) : WS_K;
 };
 
-template <typename A, int MODE, int NW>
+template <typename A, int MODE, int NW, int KROWS = 0>
 int launch_ws(sb_ctx* ctx, const A* in, A* out, size_t n, int exclusive, size_t seg_len, size_t seg_mask, const uint8_t* flags,
     const A* seed, typename Desc<A>::word* desc, uint32_t epoch, int use_lookback, size_t tiles, const unsigned long long* gate = nullptr,
     unsigned long long gate_seq = 0, int gate_want = 0) {
-  constexpr int K = ws_rows<MODE, (int)sizeof(A)>::K;
+  constexpr int K = KROWS > 0 ? KROWS : ws_rows<MODE, (int)sizeof(A)>::K;
   constexpr size_t smem = (size_t)WS_STAGES * ws_stage_bytes<A, MODE, K, NW>();
   constexpr int WS_THREADS = (NW + 2) * 32;
   static OccupancyCache ws_cache, ind_cache;
@@ -858,7 +863,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   const bool mid = mode == MODE_IMPLICIT && sizeof(A) == 8 && !narrow && sb::is_pow2(seg_len) && TileCfg<A, WS_NW, WS_K>::TILE % seg_len == 0;
   const bool lb64 = lb64_enabled && sizeof(A) == 8 && (mode == MODE_FLAGS || (mode == MODE_IMPLICIT && !narrow && !mid));
   const size_t ws_tile = mode == MODE_FLAGS ? (lb64 ? TileCfg<A, WS_NW_LB64, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE : TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE)
-                         : wide ? wide_tile : narrow ? narrow_tile : lb64 ? TileCfg<A, WS_NW_LB64, WS_K>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
+                         : wide ? wide_tile : narrow ? narrow_tile : lb64 ? TileCfg<A, WS_NW_LB64, WS_K_LB64>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
   const size_t simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
   const bool use_ws = aligned && n >= 4 * ws_tile;
   const size_t tile = use_ws ? ws_tile : simple_tile;
@@ -897,7 +902,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
     if(mode == MODE_PLAIN) rc = launch_ws<A, MODE_PLAIN, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && wide) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && narrow) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_NARROW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
-    else if(mode == MODE_IMPLICIT && lb64) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    else if(mode == MODE_IMPLICIT && lb64) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_LB64, WS_K_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT) rc = launch_ws<A, MODE_IMPLICIT, WS_NW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else {
       // explicit flags: check kernel + both scan kernels, gated by its verdict (see flags_tile_heads_kernel).
