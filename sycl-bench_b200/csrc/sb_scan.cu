@@ -82,6 +82,18 @@ constexpr int WS_NW = SB_WS_NW, WS_K = SB_WS_K, WS_STAGES = SB_WS_STAGES, WS_DEP
 #define SB_WS_NW_WIDE 18  // worker warps of the 72 KB-tile instantiations (global scans; 32-bit independent tiles)
 #endif
 constexpr int WS_NW_WIDE = SB_WS_NW_WIDE;
+// Global (plain) scans: the tile stays ~70 KB — their rate is tile bytes per look-back round — but its shape is chosen per element
+// size from a sweep at 2^28 / 2^30 (profiles/r02_ops_v21_plain_tile_shapes.jsonl; default before: 18 workers x 8 rows for all):
+//   32-bit: 16 workers x 9 rows (72 KB, 18 warps, 96 registers):  fp32 6.15 -> 6.37, int32 6.36 -> 6.34 (2^30: 6.52 -> 6.62) TB/s
+//   64-bit: 14 workers x 10 rows (70 KB, 16 warps, 128 registers): int64 6.23 -> 6.38, fp64 6.24 -> 6.32 (2^30 int64: 6.34 -> 6.42)
+//   (16 x 9 loses 7 % for 64-bit types — spills at 96 registers —, 14 x 10 loses 1-4 % for 32-bit, 12 x 12 loses everywhere)
+#ifndef SB_WS_PLAIN_SHAPE
+#define SB_WS_PLAIN_SHAPE 1  // 0: 18 x 8 for every type
+#endif
+template <int BYTES> struct plain_shape {
+  static constexpr int NW = !SB_WS_PLAIN_SHAPE ? SB_WS_NW_WIDE : BYTES == 8 ? 14 : 16;
+  static constexpr int K = !SB_WS_PLAIN_SHAPE ? SB_WS_K : BYTES == 8 ? 10 : 9;
+};
 #ifndef SB_WS_NW_NARROW
 #define SB_WS_NW_NARROW 15  // 15 workers + producer = 16 warps: 128 registers per thread for 64-bit independent tiles
 #endif
@@ -863,7 +875,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   const bool mid = mode == MODE_IMPLICIT && sizeof(A) == 8 && !narrow && sb::is_pow2(seg_len) && TileCfg<A, WS_NW, WS_K>::TILE % seg_len == 0;
   const bool lb64 = lb64_enabled && sizeof(A) == 8 && (mode == MODE_FLAGS || (mode == MODE_IMPLICIT && !narrow && !mid));
   const size_t ws_tile = mode == MODE_FLAGS ? (lb64 ? TileCfg<A, WS_NW_LB64, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE : TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE)
-                         : wide ? wide_tile : narrow ? narrow_tile : lb64 ? TileCfg<A, WS_NW_LB64, WS_K_LB64>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
+                         : mode == MODE_PLAIN ? TileCfg<A, plain_shape<sizeof(A)>::NW, plain_shape<sizeof(A)>::K>::TILE : wide ? wide_tile : narrow ? narrow_tile : lb64 ? TileCfg<A, WS_NW_LB64, WS_K_LB64>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
   const size_t simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
   const bool use_ws = aligned && n >= 4 * ws_tile;
   const size_t tile = use_ws ? ws_tile : simple_tile;
@@ -899,7 +911,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   const A* aseed = reinterpret_cast<const A*>(seed);
   if(use_ws) {
     int rc;
-    if(mode == MODE_PLAIN) rc = launch_ws<A, MODE_PLAIN, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+    if(mode == MODE_PLAIN) rc = launch_ws<A, MODE_PLAIN, plain_shape<sizeof(A)>::NW, plain_shape<sizeof(A)>::K>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && wide) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && narrow) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_NARROW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && lb64) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_LB64, WS_K_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
