@@ -497,7 +497,7 @@ def run_ours(args):
     if rank == 0:
         red = "sb_reduce_all (all-reduce inside the kernel, peer mailboxes)" if (B.peer is not None and args.reduce_exchange == "fused") else "sb_reduce + NCCL all-reduce(1 elt)"
         par = {"single": "1 GPU",
-               "cyclic": f"{world} GPUs, block-cyclic shards (block = {B.ctx.sm_count} tiles of 72 KB); reduce: {red}; prefixsum: sb_scan_cyclic, round totals over NVLink peer memory inside the kernel, 2 passes",
+               "cyclic": f"{world} GPUs, block-cyclic shards (block = {B.ctx.sm_count} tiles of 70 KB); reduce: {red}; prefixsum: sb_scan_cyclic, round totals over NVLink peer memory inside the kernel, 2 passes",
                "reduce_then_scan": f"{world} contiguous shards; reduce: {red}; prefixsum: sb_reduce -> NCCL all-gather -> seeded sb_scan, 3 passes",
                "scan_then_carry": f"{world} contiguous shards; reduce: {red}; prefixsum: sb_scan -> NCCL all-gather -> sb_carry_add, 4 passes"}[B.strategy]
         line = {

@@ -7,13 +7,13 @@
 // Why: with CONTIGUOUS shards no output of shard r can be written before every shard < r has been read completely,
 // so reduce-then-scan (sb_comm_scan / sharded.py) reads a shard twice: 3*N*s/P bytes per GPU, 0.735 weak-scaling
 // efficiency at 8 GPUs in round 1.  Here the global array is dealt to the GPUs BLOCK-CYCLICALLY in blocks of one
-// kernel round (G tiles = 148 x 72 KB = 10.4 MB): round r of rank g is block r*P + g.  Every rank runs the same
+// kernel round (G tiles = 148 x 70 KB = 10.1 MB): round r of rank g is block r*P + g.  Every rank runs the same
 // persistent kernel; per tile it does
 //   phase A (tile i + D): TMA bulk load (L2 policy evict_last) -> per-warp sums -> tile aggregate -> descriptor;
 //   phase B (tile i)    : TMA bulk load of the same tile again — it was read D rounds ago and is still in the
 //                         126 MB L2 (policy evict_first: last use) — scan with the tile prefix, 128-bit stores
 //                         (policy evict_first).  The two kinds of load alternate in one smem ring, so the distance
-//                         between the two reads of a tile is exactly D rounds (D x 10.4 MB of L2).
+//                         between the two reads of a tile is exactly D rounds (D x 10.1 MB of L2).
 // The prefix of tile (round r, rank g, position pos) is
 //      E[r]                      everything in rounds < r, on all ranks        (running sum kept by every look-back warp)
 //    + sum_{g' < g} T[r][g']     the round totals of the lower ranks           (mailbox, written by the peers)
@@ -37,11 +37,15 @@
 #include "sb_peer.cuh"
 #include "sb_scan_tile.cuh"
 
+// Tile shape: 14 workers x 10 rows x 512 B = 70 KB (16 warps with producer and look-back warp -> 128 registers per thread).
+// The first shape, 18 workers x 8 rows (72 KB, 20 warps -> 96 registers), spilled 44 bytes in the fp64 instantiation; measured
+// on one GPU at 2^28 (profiles/r02_ops_v23_cyclic_tile_shapes.jsonl): fp64 4.96 -> 6.17, int64 6.00 -> 6.26, int32 6.25 -> 6.34,
+// fp32 6.23 -> 6.26 TB/s; 16 x 9 loses 8 % for 64-bit types.
 #ifndef SB_CY_NW
-#define SB_CY_NW 18
+#define SB_CY_NW 14
 #endif
 #ifndef SB_CY_K
-#define SB_CY_K 8
+#define SB_CY_K 10
 #endif
 #ifndef SB_CY_STAGES
 #define SB_CY_STAGES 3
@@ -427,7 +431,7 @@ int scan_cyclic_impl(sb_ctx* ctx, sb_peer* peer, const T* in, T* out, size_t n, 
   }
   // look-ahead in rounds and L2 policies: defaults from the measurements in profiles/ (r02); the env knobs exist for tuning runs
   static const int env_depth = env_int("SB_CYCLIC_DEPTH", 0, 0, CY_MAX_DEPTH), env_hint = env_int("SB_CYCLIC_HINT", -1, -1, 1);
-  int D = env_depth > 0 ? env_depth : 2;  // rounds of 10.4 MB: L2 keeps ~3 of them (profiles/r02_cyclic_variants.txt); 8 GPUs: D=1/2/3 -> 7.00/7.00/6.87x on config 5
+  int D = env_depth > 0 ? env_depth : 2;  // rounds of 10.1 MB: L2 keeps ~3 of them (profiles/r02_cyclic_variants.txt); 8 GPUs: D=1/2/3 -> 7.00/7.00/6.87x on config 5
   int hint = env_hint >= 0 ? env_hint : 1;
   size_t grid = (size_t)G < tiles ? (size_t)G : tiles;
   const A* ain = reinterpret_cast<const A*>(in);

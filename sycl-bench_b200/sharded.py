@@ -8,7 +8,7 @@
                 "scan_then_carry" : local sb_scan -> all-gather of the shard totals
                                     -> sb_exclusive_carry -> sb_carry_add                    (4*N*s/P per GPU,
                                     the literal BASELINE.json north_star recipe)
-                "cyclic"          : BLOCK-CYCLIC shards (block = one round of the persistent kernel, 10.4 MB);
+                "cyclic"          : BLOCK-CYCLIC shards (block = one round of the persistent kernel, 10.1 MB);
                                     sb_scan_cyclic on every rank: the round totals cross NVLink inside the kernel
                                     (peer-memory mailboxes), nothing is read twice              (2*N*s/P per GPU,
                                     no torch.distributed call in the data path — only the one-off exchange of
