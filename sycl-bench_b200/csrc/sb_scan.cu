@@ -87,6 +87,11 @@ constexpr int WS_NW_WIDE = SB_WS_NW_WIDE;
 //   32-bit: 16 workers x 9 rows (72 KB, 18 warps, 96 registers):  fp32 6.15 -> 6.37, int32 6.36 -> 6.34 (2^30: 6.52 -> 6.62) TB/s
 //   64-bit: 14 workers x 10 rows (70 KB, 16 warps, 128 registers): int64 6.23 -> 6.38, fp64 6.24 -> 6.32 (2^30 int64: 6.34 -> 6.42)
 //   (16 x 9 loses 7 % for 64-bit types — spills at 96 registers —, 14 x 10 loses 1-4 % for 32-bit, 12 x 12 loses everywhere)
+#ifndef SB_WS_LB32_SHAPE
+#define SB_WS_LB32_SHAPE 0  // 1: 32-bit implicit heads on the look-back path take 14 workers x 10 rows (128 registers) instead of 18 x 8:
+                            // measured 15-23 % SLOWER (L = 65536 int32 5.56 -> 4.28 TB/s), with either form of phase A
+                            // (profiles/r02_ops_v24_lb32_14x10_ab.jsonl) — what helps 64-bit types and the two-phase kernel does not carry over
+#endif
 #ifndef SB_WS_PLAIN_SHAPE
 #define SB_WS_PLAIN_SHAPE 1  // 0: 18 x 8 for every type
 #endif
@@ -875,7 +880,8 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   const bool mid = mode == MODE_IMPLICIT && sizeof(A) == 8 && !narrow && sb::is_pow2(seg_len) && TileCfg<A, WS_NW, WS_K>::TILE % seg_len == 0;
   const bool lb64 = lb64_enabled && sizeof(A) == 8 && (mode == MODE_FLAGS || (mode == MODE_IMPLICIT && !narrow && !mid));
   const size_t ws_tile = mode == MODE_FLAGS ? (lb64 ? TileCfg<A, WS_NW_LB64, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE : TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE)
-                         : mode == MODE_PLAIN ? TileCfg<A, plain_shape<sizeof(A)>::NW, plain_shape<sizeof(A)>::K>::TILE : wide ? wide_tile : narrow ? narrow_tile : lb64 ? TileCfg<A, WS_NW_LB64, WS_K_LB64>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
+                         : mode == MODE_PLAIN ? TileCfg<A, plain_shape<sizeof(A)>::NW, plain_shape<sizeof(A)>::K>::TILE
+                         : (SB_WS_LB32_SHAPE && implicit32_lookback) ? TileCfg<A, 14, 10>::TILE : wide ? wide_tile : narrow ? narrow_tile : lb64 ? TileCfg<A, WS_NW_LB64, WS_K_LB64>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
   const size_t simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
   const bool use_ws = aligned && n >= 4 * ws_tile;
   const size_t tile = use_ws ? ws_tile : simple_tile;
@@ -912,6 +918,9 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   if(use_ws) {
     int rc;
     if(mode == MODE_PLAIN) rc = launch_ws<A, MODE_PLAIN, plain_shape<sizeof(A)>::NW, plain_shape<sizeof(A)>::K>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+#if SB_WS_LB32_SHAPE
+    else if(implicit32_lookback) rc = launch_ws<A, MODE_IMPLICIT, 14, 10>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
+#endif
     else if(mode == MODE_IMPLICIT && wide) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_WIDE>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && narrow) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_NARROW>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);
     else if(mode == MODE_IMPLICIT && lb64) rc = launch_ws<A, MODE_IMPLICIT, WS_NW_LB64, WS_K_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles);

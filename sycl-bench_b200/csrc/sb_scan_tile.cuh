@@ -242,7 +242,11 @@ __device__ __forceinline__ void warp_reduce_rows(const A (&v)[K][16 / sizeof(A)]
 #ifdef SB_SCAN_PHASEA_PER_ROW
       true;
 #else
+#ifdef SB_SCAN_PHASEA_PER_CHUNK32
+      false;
+#else
       MODE == MODE_IMPLICIT && sizeof(A) == 4;
+#endif
 #endif
   if(PER_ROW) {
     // one warp sum per row (K x 5 shuffles), restarted at the last head of a row
