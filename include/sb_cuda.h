@@ -292,7 +292,7 @@ int sb_comm_foreach(sb_comm* comm, int op, int dtype, const void* const* in, voi
 
 /* ---- block-cyclic prefix sum: one read of the input per GPU, exchange inside the kernel ------------------------ */
 /* The global array is dealt to the `world` ranks in blocks of sb_cyclic_block_elems() elements (one round of the
- * persistent kernel: sm_count tiles of 72 KB): block k lives on rank k % world, a rank stores its blocks back to
+ * persistent kernel: sm_count tiles of 70 KB): block k lives on rank k % world, a rank stores its blocks back to
  * back, every rank holds the same number n of elements (the blocks of the last round may be short: they all have
  * n - floor(n / block) * block elements).  Global index of local element i of rank g, with b = i / block:
  *     b < n / block :  (b * world + g) * block + i % block
