@@ -870,7 +870,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   // warps ptxas has 96 and spills (fp64 group scan 5.5 -> 6.4 TB/s)
   constexpr size_t narrow_tile = TileCfg<A, WS_NW_NARROW, WS_K>::TILE;
   const bool narrow = mode == MODE_IMPLICIT && sizeof(A) == 8 && sb::is_pow2(seg_len) && narrow_tile % seg_len == 0;
-  // 64-bit types on the look-back kernel in a segmented mode: 14 workers + producer + look-back = 16 warps, so that a
+  // 64-bit types on the look-back kernel with implicit heads: 14 workers + producer + look-back = 16 warps, so that a
   // thread may use 128 registers (at 18 warps ptxas has 96 and spills 100-270 bytes, profiles/r02_ptxas_spills.txt).
   // SB_SCAN_LB64_NW=16 keeps the 16-worker instantiation (A/B measurements).
   static const bool lb64_enabled = !(getenv("SB_SCAN_LB64_NW") && atoi(getenv("SB_SCAN_LB64_NW")) == 16);
@@ -878,8 +878,9 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
   // 16 x 8 rows (8192) is — independent tiles with 16 workers (96 registers, a few spills) still beat the look-back kernel
   // by a wide margin (L = 16384 on the look-back path measured 3.0 TB/s against 5.5-6.6 for independent tiles)
   const bool mid = mode == MODE_IMPLICIT && sizeof(A) == 8 && !narrow && sb::is_pow2(seg_len) && TileCfg<A, WS_NW, WS_K>::TILE % seg_len == 0;
-  const bool lb64 = lb64_enabled && sizeof(A) == 8 && (mode == MODE_FLAGS || (mode == MODE_IMPLICIT && !narrow && !mid));
-  const size_t ws_tile = mode == MODE_FLAGS ? (lb64 ? TileCfg<A, WS_NW_LB64, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE : TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE)
+  // (explicit flags run 14 workers for every type, see SB_WS_NW_FLAGS)
+  const bool lb64 = lb64_enabled && sizeof(A) == 8 && mode == MODE_IMPLICIT && !narrow && !mid;
+  const size_t ws_tile = mode == MODE_FLAGS ? TileCfg<A, WS_NW_FLAGS, ws_rows<MODE_FLAGS, (int)sizeof(A)>::K>::TILE
                          : mode == MODE_PLAIN ? TileCfg<A, plain_shape<sizeof(A)>::NW, plain_shape<sizeof(A)>::K>::TILE
                          : (SB_WS_LB32_SHAPE && implicit32_lookback) ? TileCfg<A, 14, 10>::TILE : wide ? wide_tile : narrow ? narrow_tile : lb64 ? TileCfg<A, WS_NW_LB64, WS_K_LB64>::TILE : TileCfg<A, WS_NW, WS_K>::TILE;
   const size_t simple_tile = TileCfg<A, SCAN_NT / 32, SCAN_K>::TILE;
@@ -937,14 +938,10 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
         seq = ++ctx->flags_gate_seq;
         flags_tile_heads_kernel<<<(unsigned)((tiles + 254) / 256), 256, 0, ctx->stream>>>(flags, (long long)tiles, tile, g, seq);
         gate = g;
-        // (64-bit types keep the 14-worker tile here too: 15 workers x 6 rows x 64 elements is not a multiple of 256)
-        if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, seq, 0);
-        else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, seq, 0);
+        // (both kernels of the pair share one tile size: 14 workers x 8 rows, a multiple of 256 elements for every type)
+        rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, seq, 0);
       }
-      if(rc == SB_OK) {
-        if(lb64) rc = launch_ws<A, MODE_FLAGS, WS_NW_LB64>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles, gate, seq, 1);
-        else rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles, gate, seq, 1);
-      }
+      if(rc == SB_OK) rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, use_lookback, tiles, gate, seq, 1);
     }
     if(rc != SB_OK) return rc;
     SB_CHECK_LAUNCH(ctx);
