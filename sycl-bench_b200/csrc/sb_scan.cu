@@ -938,6 +938,7 @@ int scan_launch(sb_ctx* ctx, const T* in, T* out, size_t n, int exclusive, int m
         seq = ++ctx->flags_gate_seq;
         flags_tile_heads_kernel<<<(unsigned)((tiles + 254) / 256), 256, 0, ctx->stream>>>(flags, (long long)tiles, tile, g, seq);
         gate = g;
+        ctx->launches += 2;  // the check and the kernel of the pair that leaves at once are launches too (sb_ctx_launch_count)
         // (both kernels of the pair share one tile size: 14 workers x 8 rows, a multiple of 256 elements for every type)
         rc = launch_ws<A, MODE_FLAGS, WS_NW_FLAGS>(ctx, ain, aout, n, exclusive, seg_len, seg_mask, flags, aseed, desc, epoch, 0, tiles, gate, seq, 0);
       }
