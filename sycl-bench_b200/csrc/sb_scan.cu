@@ -33,6 +33,14 @@
 //    32 tiles, nobody waits for a neighbour's look-back, and the summation order is fixed
 //    (deterministic floating point).
 //
+//  scan_independent_kernel: the same ring and worker code without descriptors and look-back warp, tiles handed out in
+//    order by an atomic ticket — whenever every tile starts on a segment head (implicit heads with a power-of-two
+//    segment that divides the tile; explicit flags after flags_tile_heads_kernel has said so on the device).
+//
+//  Tile shapes (workers x rows of 512 B, chosen per case from measurements; see the knobs below): plain scans 16 x 9
+//    (32-bit) / 14 x 10 (64-bit); implicit heads 18 x 8 or 15 / 16 x 8 (independent tiles), 18 x 8 / 14 x 8 (look-back);
+//    explicit flags 14 x 8 with the tile's flag bytes in the same ring stage.
+//
 //  scan_kernel (unaligned or tiny inputs): one CTA per 16 KB tile, tile ids from an atomic ticket,
 //    classic windowed look-back.
 //
